@@ -1,0 +1,200 @@
+"""Network blocks of the DH3D forward pass, point-major, inference only.
+
+Mirrors ``core/backbones.py`` + the glue of ``core/tf_utils.py`` of the reference; module and
+parameter names follow the reference's TF variable scopes with '/' -> '.':
+
+    subsample                 core/tf_utils.py:86-96      FPS + group_point
+    feature_conv1d_1          core/tf_utils.py:99-109     -> FeatureConv1d ('<name>/tfconv0/{W,b,bn}')
+    flexconv_withBatchnorm    core/tf_utils.py:48-64      -> FlexConvolution + '<name>_bn', fused ReLU
+    se_res_bottleneck         core/backbones.py:45-55     -> SEBlock
+    flex_conv_dilate          core/backbones.py:58-101    -> FlexConvDilate
+    backbone_local_dilate     core/backbones.py:104-127   -> LocalBackbone
+    detection_block           core/backbones.py:132-151   -> DetectionBlock
+    globalatt_block           core/backbones.py:156-173   -> GlobalAttBlock
+    global_netvald_block      core/backbones.py:202-279   -> GlobalNetVLADBlock (+ context_gating :282-320)
+
+One structural difference from the reference graph: FPS, the k-NN of the sampled points and the
+3-NN of the dense points depend only on xyz, and ``stage2`` and ``global_before_assemble`` both
+use dilate 8 on the same xyz, so they are computed ONCE per cloud (``DilateGeometry``) and shared
+(the reference recomputes them).
+"""
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+from .layers import (SLIM_BN_EPS, BatchNorm, Conv1x1, ConvolutionPointset, FlexConvolution,
+                     FlexPooling)
+
+
+class DilateGeometry(object):
+    """Everything ``flex_conv_dilate(dilate > 1)`` derives from xyz alone."""
+
+    def __init__(self, xyz, npoint, knn):
+        self.kp_indices = ops.farthest_point_sample(npoint, xyz)              # [B,M]
+        self.points_sampled = ops.gather_point(xyz, self.kp_indices)          # [B,M,3]
+        self.knn_indices, _ = ops.knn_points(self.points_sampled, knn)        # [B,M,K]
+        self.nn_dist, self.nn_idx = ops.three_nn(xyz, self.points_sampled)    # [B,N,3] x2
+
+
+def subsample(points, feat, targetnum, kp_idx=None):
+    """core/tf_utils.py:86-96 -> (xyz_sampled [B,M,3], feat_sampled [B,M,C], kp_indices [B,M,1])."""
+    if kp_idx is None:
+        kp_idx = ops.farthest_point_sample(targetnum, points).unsqueeze(2)
+    kp_idx = kp_idx.contiguous()
+    feat_sampled = ops.group_point(feat, kp_idx).squeeze(2)
+    xyz_sampled = ops.group_point(points, kp_idx).squeeze(2)
+    return xyz_sampled, feat_sampled, kp_idx
+
+
+class FeatureConv1d(nn.Module):
+    """feature_conv1d_1(feat, dim, name, ac_func): variables under '<name>/tfconv0'."""
+
+    def __init__(self, cin, cout, bn=True, act=ACT_RELU):
+        super().__init__()
+        self.tfconv0 = Conv1x1(cin, cout, bn=bn, act=act)
+
+    def forward(self, x, out=None, out_col=0):
+        return self.tfconv0(x, out=out, out_col=out_col)
+
+
+class SEBlock(nn.Module):
+    """se_res_bottleneck: per-point squeeze/excite computed from the POOLED features (no global
+    pooling): gate = sigmoid(W2 relu(W1 pool + b1) + b2); out = relu(x + x*gate)."""
+
+    def __init__(self, ch):
+        super().__init__()
+        self.f1 = FeatureConv1d(ch, ch // 4, bn=False, act=ACT_RELU)
+        self.f2 = FeatureConv1d(ch // 4, ch, bn=False, act=ACT_SIGMOID)
+
+    def forward(self, x, pooled):
+        return ops.se_excite(x, self.f2(self.f1(pooled)))
+
+
+class FlexConvDilate(nn.Module):
+    def __init__(self, cin, outdims, dilate, knn=8, concat=True, add_se="max_pool", upsample=True):
+        super().__init__()
+        assert add_se in ("max_pool", "")
+        self.dilate, self.knn, self.upsample = dilate, knn, upsample
+        self.outdims = list(outdims)
+        c = cin
+        for i, d in enumerate(outdims):
+            setattr(self, "flexconv_%d" % i, FlexConvolution(c, d))
+            setattr(self, "flexconv_%d_bn" % i, BatchNorm(d))
+            c = d
+        self.se = SEBlock(c) if add_se == "max_pool" else None
+        self.concat_conv1d = FeatureConv1d(c + cin, c) if concat else None
+
+    def forward(self, xyz, feat, knn_indices=None, geometry=None):
+        """xyz [B,N,3], feat [B,N,C] -> new_feat [B,N,outdims[-1]]."""
+        if self.dilate > 1:
+            g = geometry or DilateGeometry(xyz, xyz.shape[1] // self.dilate, self.knn)
+            pts = g.points_sampled
+            x = ops.group_point(feat, g.kp_indices.unsqueeze(2)).squeeze(2)
+            nbr = g.knn_indices
+        else:
+            g, pts, x = None, xyz, feat
+            nbr = knn_indices if knn_indices is not None else ops.knn_points(xyz, self.knn)[0]
+        for i in range(len(self.outdims)):
+            x = getattr(self, "flexconv_%d" % i).forward_pm(
+                x, pts, nbr, bn=getattr(self, "flexconv_%d_bn" % i), act=ACT_RELU)
+        if self.se is not None:
+            x = self.se(x, ops.flex_pool(x, nbr))
+        if self.upsample and self.dilate > 1:
+            x = ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True)
+        if self.concat_conv1d is not None:
+            B, N, C = x.shape
+            cat = torch.empty((B, N, C + feat.shape[2]), dtype=x.dtype, device=x.device)
+            ops.copy_cols(x, cat, 0)
+            ops.copy_cols(feat, cat, C)
+            x = self.concat_conv1d(cat)
+        return x
+
+
+class LocalBackbone(nn.Module):
+    """backbone_local_dilate (featdim == 128: no final_fc)."""
+
+    def __init__(self, init_feat_dim=32, featdim=128, dilate2=8, knn=8):
+        super().__init__()
+        assert featdim == 128, "featdim < 128 (final_fc) is not part of the shipped configs"
+        self.knn = knn
+        self.initconv = ConvolutionPointset(3, init_feat_dim)
+        self.initconv_bn = BatchNorm(init_feat_dim)
+        self.stage1 = FlexConvDilate(init_feat_dim, [64, 64], dilate=1, knn=knn, concat=False)
+        self.before_stage2_conv1d = FeatureConv1d(64, 64)
+        self.stage2 = FlexConvDilate(64, [128, 128], dilate=dilate2, knn=knn, concat=True)
+        self.local_stage1_shortcut = FeatureConv1d(64, 128)
+
+    def forward(self, points, knn_ind, geometry=None):
+        nn_8 = knn_ind if knn_ind.shape[2] == 8 else knn_ind[:, :, :8].contiguous()
+        f = self.initconv.forward_pm(points, nn_8, bn=self.initconv_bn, act=ACT_RELU)
+        f = ops.flex_pool(f, nn_8)
+        x1 = self.stage1(points, f, knn_indices=nn_8)
+        x2 = self.before_stage2_conv1d(x1)
+        x2 = self.stage2(points, x2, geometry=geometry)
+        return ops.add(self.local_stage1_shortcut(x1), x2)
+
+
+class AttentionHead(nn.Module):
+    """1x1 stack -> 1 logit -> sigmoid.  detection_block: 128->128->256->1024->1;
+    globalatt_block: 256->1024->1."""
+
+    def __init__(self, cin, conv_dims):
+        super().__init__()
+        c = cin
+        self.n = len(conv_dims)
+        for i, d in enumerate(conv_dims):
+            setattr(self, "detec_conv%d" % i, Conv1x1(c, d, bn=True, act=ACT_RELU))
+            c = d
+        self.detec_conv_fc = Conv1x1(c, 1, bn=False, act=ACT_NONE)
+        self._folded = None
+
+    def forward(self, x):
+        for i in range(self.n):
+            x = getattr(self, "detec_conv%d" % i)(x)
+        if self._folded is None:
+            fc = self.detec_conv_fc
+            self._folded = (fc.W.reshape(-1).contiguous(), float(fc.b.reshape(-1)[0].item()))
+        w, b = self._folded
+        return ops.rowdot(x, w, bias=b, act=ACT_SIGMOID).unsqueeze(-1)  # [B,N,1]
+
+
+class DetectionBlock(AttentionHead):
+    def __init__(self, cin=128, conv_dims=(128, 256, 1024)):
+        super().__init__(cin, conv_dims)
+
+
+class GlobalAttBlock(AttentionHead):
+    def __init__(self, cin=256):
+        super().__init__(cin, (256, 1024) if cin > 256 else (1024,))
+
+
+class GlobalNetVLADBlock(nn.Module):
+    """global_netvald_block(xyz, features, att, is_training, cluster_size=64, output_dim=256,
+    add_batch_norm=True, gating=True) -- variables live at the root scope in the checkpoint."""
+
+    def __init__(self, feature_size=256, cluster_size=64, output_dim=256):
+        super().__init__()
+        z = lambda *s: nn.Parameter(torch.zeros(*s), requires_grad=False)
+        self.cluster_weights = z(feature_size, cluster_size)
+        self.cluster_weights2 = z(1, feature_size, cluster_size)
+        self.cluster_bn = BatchNorm(cluster_size, eps=SLIM_BN_EPS)
+        self.hidden1_weights = z(cluster_size * feature_size, output_dim)
+        self.bn = BatchNorm(output_dim, eps=SLIM_BN_EPS)
+        self.gating_weights = z(output_dim, output_dim)
+        self.gating_bn = BatchNorm(output_dim, eps=SLIM_BN_EPS)
+        self._folded = None
+
+    def forward(self, xyz, features, att, final_l2norm=True):
+        if self._folded is None:
+            self._folded = (self.cluster_bn.fold(), self.bn.fold(), self.gating_bn.fold(),
+                            self.cluster_weights2.reshape(self.cluster_weights.shape).contiguous())
+        cbn, bn, gbn, cw2 = self._folded
+        return ops.netvlad(features, att, self.cluster_weights, cbn, cw2, self.hidden1_weights, bn,
+                           self.gating_weights, gbn, final_l2norm=final_l2norm)
+
+
+def global_netvald_block(block, xyz, features, att, is_training=False, **unused):
+    """Function form with the reference's argument order (core/backbones.py:202)."""
+    assert not is_training, "inference only"
+    return block(xyz, features, att, final_l2norm=False)

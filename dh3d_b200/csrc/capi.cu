@@ -1,0 +1,225 @@
+// extern "C" surface of libdh3d_b200.so -- see include/dh3d_b200.h for the contract and the
+// reference interface (file:line) each entry point replaces.
+#include "common.cuh"
+
+namespace dh3d {
+// knn.cu
+size_t knn_workspace_bytes(int B, int N);
+int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
+               float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// fps.cu
+int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st);
+// gather.cu
+int group_point_launch(int b, int n, int c, int m, int s, const float* points, const int32_t* idx,
+                       float* out, cudaStream_t st);
+int flex_pool_pm_launch(const float* feat, const int32_t* nbr, float* out, int32_t* argmax, int B,
+                        int N, int K, int D, cudaStream_t st);
+int flex_pool_cm_launch(const float* feat, const int32_t* nbr, float* out, int32_t* argmax, int B,
+                        int N, int K, int D, cudaStream_t st);
+int conv_pointset_pm_launch(const float* feat, const float* theta, const float* bias,
+                            const int32_t* nbr, float* out, int B, int N, int K, int Din, int Dout,
+                            const float* scale, const float* shift, int act, cudaStream_t st);
+int conv_pointset_cm_launch(const float* feat, const float* theta, const float* bias,
+                            const int32_t* nbr, float* out, int B, int N, int K, int Din, int Dout,
+                            cudaStream_t st);
+int three_nn_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                    int32_t* idx, cudaStream_t st);
+int three_interpolate_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                             const float* wsrc, float* out, bool from_dist, cudaStream_t st);
+size_t query_ball_workspace_bytes(int b, int m);
+int query_ball_launch(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                      const float* xyz2, int32_t* idx, int32_t* pts_cnt, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
+int transpose_launch(const void* src, void* dst, int B, int R, int C, cudaStream_t st);
+int se_excite_launch(const float* x, const float* g, float* y, size_t count, cudaStream_t st);
+int add_launch(const float* a, const float* b, float* y, size_t count, cudaStream_t st);
+int copy_cols_launch(const float* src, int lds, float* dst, int ldd, int M, int C, cudaStream_t st);
+int l2norm_rows_launch(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
+                       cudaStream_t st);
+int rowdot_launch(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
+                  int K, cudaStream_t st);
+// gemm_simt.cu
+int linear_simt_launch(const float* x, int ldx, const float* w, const float* scale,
+                       const float* shift, int act, float* y, int ldy, int M, int K, int N,
+                       cudaStream_t st);
+// flexconv.cu
+size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout);
+size_t flex_conv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int flex_conv_pm(const float* feat, const float* theta, const float* bias, const int32_t* nbr,
+                 const float* xyz, float* out, int B, int N, int K, int Din, int Dout,
+                 const float* feature_bias, const float* scale, const float* shift, int act,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+int flex_conv_cm(const float* feat_cm, const float* theta, const float* bias, const int32_t* nbr_cm,
+                 const float* pos_cm, float* out_cm, int B, int N, int K, int Din, int Dout, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+// netvlad.cu
+size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim);
+int netvlad_launch(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
+                   const float* cw, const float* cbn_scale, const float* cbn_shift, const float* cw2,
+                   const float* hw, const float* bn_scale, const float* bn_shift, const float* gw,
+                   const float* gbn_scale, const float* gbn_shift, int final_l2norm, float* out,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
+
+// GEMM dispatch (one place to switch the dense path)
+int linear_launch(const float* x, int ldx, const float* w, const float* scale, const float* shift,
+                  int act, float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+  return linear_simt_launch(x, ldx, w, scale, shift, act, y, ldy, M, K, N, st);
+}
+}  // namespace dh3d
+
+using namespace dh3d;
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int dh3d_version(void) { return 100; }
+
+const char* dh3d_error_string(int code) {
+  switch (code) {
+    case DH3D_OK: return "ok";
+    case DH3D_ERR_NULL: return "a required pointer is NULL";
+    case DH3D_ERR_DIM: return "a dimension is <= 0 or inconsistent";
+    case DH3D_ERR_UNSUPPORTED: return "size or attribute outside the supported range";
+    case DH3D_ERR_WORKSPACE: return "workspace missing or too small";
+    case DH3D_ERR_ALIGN: return "pointer not 16-byte aligned";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown dh3d error";
+  }
+}
+
+size_t dh3d_knn_workspace_bytes(int B, int N) { return knn_workspace_bytes(B, N); }
+
+int dh3d_knn_bruteforce(const float* positions_cm, int B, int Dp, int N, int K, int32_t* ids,
+                        float* dists, void* workspace, size_t workspace_bytes, void* stream) {
+  if (Dp != 3) return Dp <= 0 ? DH3D_ERR_DIM : DH3D_ERR_UNSUPPORTED;
+  return knn_launch(positions_cm, B, N, K, 3LL * N, 1, N, ids, dists, workspace, workspace_bytes,
+                    S(stream));
+}
+
+int dh3d_knn_bruteforce_pm(const float* xyz_pm, int B, int N, int K, int32_t* ids, float* dists,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  return knn_launch(xyz_pm, B, N, K, 3LL * N, 3, 1, ids, dists, workspace, workspace_bytes,
+                    S(stream));
+}
+
+size_t dh3d_flex_conv_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_conv_cm_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_conv(const float* features_cm, const float* theta, const float* bias,
+                   const int32_t* neighborhood_cm, const float* positions_cm, float* out_cm, int B,
+                   int N, int K, int Din, int Dout, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  return flex_conv_cm(features_cm, theta, bias, neighborhood_cm, positions_cm, out_cm, B, N, K, Din,
+                      Dout, workspace, workspace_bytes, S(stream));
+}
+size_t dh3d_flex_conv_pm_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_conv_pm_total_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_conv_pm(const float* features_pm, const float* theta, const float* bias,
+                      const int32_t* neighborhood_pm, const float* xyz_pm, float* out_pm, int B,
+                      int N, int K, int Din, int Dout, const float* feature_bias,
+                      const float* scale, const float* shift, int act, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return flex_conv_pm(features_pm, theta, bias, neighborhood_pm, xyz_pm, out_pm, B, N, K, Din, Dout,
+                      feature_bias, scale, shift, act, workspace, workspace_bytes, S(stream));
+}
+
+int dh3d_flex_pool(const float* features_cm, const int32_t* neighborhood_cm, float* out_cm,
+                   int32_t* argmax_cm, int B, int N, int K, int D, void* stream) {
+  return flex_pool_cm_launch(features_cm, neighborhood_cm, out_cm, argmax_cm, B, N, K, D, S(stream));
+}
+int dh3d_flex_pool_pm(const float* features_pm, const int32_t* neighborhood_pm, float* out_pm,
+                      int32_t* argmax_pm, int B, int N, int K, int D, void* stream) {
+  return flex_pool_pm_launch(features_pm, neighborhood_pm, out_pm, argmax_pm, B, N, K, D, S(stream));
+}
+
+int dh3d_conv_pointset(const float* features_cm, const float* theta, const float* bias,
+                       const int32_t* neighborhood_cm, float* out_cm, int B, int N, int K, int Din,
+                       int Dout, void* stream) {
+  return conv_pointset_cm_launch(features_cm, theta, bias, neighborhood_cm, out_cm, B, N, K, Din,
+                                 Dout, S(stream));
+}
+int dh3d_conv_pointset_pm(const float* features_pm, const float* theta, const float* bias,
+                          const int32_t* neighborhood_pm, float* out_pm, int B, int N, int K,
+                          int Din, int Dout, const float* scale, const float* shift, int act,
+                          void* stream) {
+  return conv_pointset_pm_launch(features_pm, theta, bias, neighborhood_pm, out_pm, B, N, K, Din,
+                                 Dout, scale, shift, act, S(stream));
+}
+
+int dh3d_farthest_point_sample(int b, int n, int m, const float* inp, int32_t* out, void* stream) {
+  return fps_launch(b, n, m, inp, out, S(stream));
+}
+int dh3d_gather_point(int b, int n, int m, const float* inp, const int32_t* idx, float* out,
+                      void* stream) {
+  return group_point_launch(b, n, 3, m, 1, inp, idx, out, S(stream));
+}
+int dh3d_group_point(int b, int n, int c, int m, int nsample, const float* points,
+                     const int32_t* idx, float* out, void* stream) {
+  return group_point_launch(b, n, c, m, nsample, points, idx, out, S(stream));
+}
+size_t dh3d_query_ball_point_workspace_bytes(int b, int m) { return query_ball_workspace_bytes(b, m); }
+int dh3d_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                          const float* xyz2, int32_t* idx, int32_t* pts_cnt, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return query_ball_launch(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, workspace,
+                           workspace_bytes, S(stream));
+}
+int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                  int32_t* idx, void* stream) {
+  return three_nn_launch(b, n, m, xyz1, xyz2, dist, idx, S(stream));
+}
+int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                           const float* weight, float* out, void* stream) {
+  return three_interpolate_launch(b, m, c, n, points, idx, weight, out, false, S(stream));
+}
+int dh3d_three_interpolate_from_dist(int b, int m, int c, int n, const float* points,
+                                     const int32_t* idx, const float* dist2, float* out,
+                                     void* stream) {
+  return three_interpolate_launch(b, m, c, n, points, idx, dist2, out, true, S(stream));
+}
+
+int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, const float* shift,
+                int act, float* y, int ldy, int M, int K, int N, void* stream) {
+  return linear_launch(x, ldx, w, scale, shift, act, y, ldy, M, K, N, S(stream));
+}
+int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
+                int K, void* stream) {
+  return rowdot_launch(x, ldx, w, bias, act, y, M, K, S(stream));
+}
+int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream) {
+  return se_excite_launch(x, gate, y, count, S(stream));
+}
+int dh3d_l2_normalize_rows(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
+                           void* stream) {
+  return l2norm_rows_launch(x, ldx, y, ldy, M, C, eps, S(stream));
+}
+int dh3d_add(const float* a, const float* b, float* y, size_t count, void* stream) {
+  return add_launch(a, b, y, count, S(stream));
+}
+int dh3d_copy_cols(const float* src, int lds, float* dst, int ldd, int M, int C, void* stream) {
+  return copy_cols_launch(src, lds, dst, ldd, M, C, S(stream));
+}
+int dh3d_transpose_cm_to_pm(const void* src_cm, void* dst_pm, int B, int C, int N, void* stream) {
+  return transpose_launch(src_cm, dst_pm, B, C, N, S(stream));
+}
+int dh3d_transpose_pm_to_cm(const void* src_pm, void* dst_cm, int B, int N, int C, void* stream) {
+  return transpose_launch(src_pm, dst_cm, B, N, C, S(stream));
+}
+
+size_t dh3d_netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
+  return netvlad_workspace_bytes(B, N, D, Kc, out_dim);
+}
+int dh3d_netvlad(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
+                 const float* cluster_weights, const float* cluster_bn_scale,
+                 const float* cluster_bn_shift, const float* cluster_weights2,
+                 const float* hidden1_weights, const float* bn_scale, const float* bn_shift,
+                 const float* gating_weights, const float* gating_bn_scale,
+                 const float* gating_bn_shift, int final_l2norm, float* out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return netvlad_launch(features, att, B, N, D, Kc, out_dim, cluster_weights, cluster_bn_scale,
+                        cluster_bn_shift, cluster_weights2, hidden1_weights, bn_scale, bn_shift,
+                        gating_weights, gating_bn_scale, gating_bn_shift, final_l2norm, out,
+                        workspace, workspace_bytes, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// Attention-weighted NetVLAD (reference: core/backbones.py:202-279 global_netvald_block +
+// :282-320 context_gating; ~15 TF library ops that write/read the [B*N,64] assignment ~6x and
+// the [B*N,256] features 3x).
+//
+// Here the per-point work is ONE kernel that reads each feature row once and never writes a
+// per-point tensor:  l2-normalise row -> 256x64 assignment (+folded cluster BN) -> softmax(64)
+// -> x attention -> accumulate  V[d,k] += a[n,k]*x[n,d]  and  S[k] += a[n,k]  in registers.
+// Each CTA reduces a slab of points; slabs are combined deterministically (no float atomics) by
+// the small finalize kernel, which also does  V - S*W2, the per-cluster and global l2 norms and
+// the feature-major flatten.  The 16384x256 projection is a split-K GEMV-like kernel (weights are
+// read exactly once per batch), and the head kernel applies BN, context gating and the final
+// l2-normalise.
+//   D == 256 features, Kc == 64 clusters, out_dim == 256 (the shipped DH3D configuration).
+#include "common.cuh"
+
+namespace dh3d {
+
+constexpr int kVD = 256;    // feature dim == threads per CTA
+constexpr int kVK = 64;     // clusters
+constexpr int kVTP = 32;    // points per sub-tile
+constexpr int kVXS = kVD + 4;  // padded row stride of the x tile (floats)
+constexpr int kVSlabs = 16;    // CTAs (slabs of points) per cloud
+constexpr int kVSlice = 128;   // rows of hidden1_weights per projection CTA
+
+struct __align__(16) VladSmem {
+  float w[kVD][kVK];        // cluster_weights           64 KB
+  float x[kVTP][kVXS];      // normalised feature tile    32.5 KB
+  float a[kVTP][kVK];       // attention-weighted assign   8 KB
+};
+
+__global__ void __launch_bounds__(kVD)
+netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict__ att, int N,
+                         const float* __restrict__ cw, const float* __restrict__ bn_scale,
+                         const float* __restrict__ bn_shift, float* __restrict__ part_v,
+                         float* __restrict__ part_s) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  VladSmem& sm = *reinterpret_cast<VladSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int per = (N + kVSlabs - 1) / kVSlabs;
+  const int n_begin = slab * per;
+  const int n_end = min(N, n_begin + per);
+
+  for (int i = tid; i < kVD * kVK / 4; i += kVD)
+    reinterpret_cast<float4*>(&sm.w[0][0])[i] = ldg4(cw + i * 4);
+
+  float acc[kVK];
+#pragma unroll
+  for (int k = 0; k < kVK; ++k) acc[k] = 0.f;
+  float ssum = 0.f;  // threads 0..63: S[k]
+
+  // assignment GEMM thread mapping: rows 2*ty, 2*ty+1; cols 4*tx .. 4*tx+3
+  const int tx = tid & 15, ty = tid >> 4;
+  float4 bsc = ldg4(bn_scale + tx * 4), bsh = ldg4(bn_shift + tx * 4);
+
+  for (int n0 = n_begin; n0 < n_end; n0 += kVTP) {
+    const int cnt = min(kVTP, n_end - n0);
+    __syncthreads();  // previous tile fully consumed (also covers the sm.w fill on the first pass)
+    // (a) load + l2-normalise rows: warp w owns rows w*4 .. w*4+3
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = warp * 4 + rr;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (r < cnt) {
+        const float* src = feat + ((long long)b * N + n0 + r) * kVD;
+        v0 = ldg4(src + lane * 4);
+        v1 = ldg4(src + 128 + lane * 4);
+      }
+      float ss = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y +
+                 v1.z * v1.z + v1.w * v1.w;
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(fmaxf(ss, 1e-12f));  // tf.nn.l2_normalize default epsilon
+      v0.x *= inv; v0.y *= inv; v0.z *= inv; v0.w *= inv;
+      v1.x *= inv; v1.y *= inv; v1.z *= inv; v1.w *= inv;
+      *reinterpret_cast<float4*>(&sm.x[r][lane * 4]) = v0;
+      *reinterpret_cast<float4*>(&sm.x[r][128 + lane * 4]) = v1;
+    }
+    __syncthreads();
+    // (b) assignment logits for 2 rows x 4 clusters per thread
+    float l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int d = 0; d < kVD; ++d) {
+      const float a0 = sm.x[2 * ty][d], a1 = sm.x[2 * ty + 1][d];
+      const float4 w4 = *reinterpret_cast<const float4*>(&sm.w[d][tx * 4]);
+      l0[0] = fmaf(a0, w4.x, l0[0]); l0[1] = fmaf(a0, w4.y, l0[1]);
+      l0[2] = fmaf(a0, w4.z, l0[2]); l0[3] = fmaf(a0, w4.w, l0[3]);
+      l1[0] = fmaf(a1, w4.x, l1[0]); l1[1] = fmaf(a1, w4.y, l1[1]);
+      l1[2] = fmaf(a1, w4.z, l1[2]); l1[3] = fmaf(a1, w4.w, l1[3]);
+    }
+    // (c) folded cluster BN, softmax over the 64 clusters (16 lanes x 4), x attention
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float* l = h ? l1 : l0;
+      l[0] = fmaf(l[0], bsc.x, bsh.x); l[1] = fmaf(l[1], bsc.y, bsh.y);
+      l[2] = fmaf(l[2], bsc.z, bsh.z); l[3] = fmaf(l[3], bsc.w, bsh.w);
+      float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float e0 = __expf(l[0] - mx), e1 = __expf(l[1] - mx), e2 = __expf(l[2] - mx),
+            e3 = __expf(l[3] - mx);
+      float sum = (e0 + e1) + (e2 + e3);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const int r = 2 * ty + h;
+      float scale = 0.f;
+      if (r < cnt) scale = __ldg(att + (long long)b * N + n0 + r) / sum;
+      *reinterpret_cast<float4*>(&sm.a[r][tx * 4]) =
+          make_float4(e0 * scale, e1 * scale, e2 * scale, e3 * scale);
+    }
+    __syncthreads();
+    // (d) V[d=tid, :] += a[n, :] * x[n, d];  S[k] += a[n, k]
+    for (int n = 0; n < cnt; ++n) {
+      const float xv = sm.x[n][tid];
+#pragma unroll
+      for (int k = 0; k < kVK; k += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&sm.a[n][k]);
+        acc[k] = fmaf(a4.x, xv, acc[k]); acc[k + 1] = fmaf(a4.y, xv, acc[k + 1]);
+        acc[k + 2] = fmaf(a4.z, xv, acc[k + 2]); acc[k + 3] = fmaf(a4.w, xv, acc[k + 3]);
+      }
+      if (tid < kVK) ssum += sm.a[n][tid];
+    }
+  }
+
+  float* pv = part_v + (((long long)b * kVSlabs + slab) * kVD + tid) * kVK;
+#pragma unroll
+  for (int k = 0; k < kVK; k += 4)
+    *reinterpret_cast<float4*>(pv + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+  if (tid < kVK) part_s[((long long)b * kVSlabs + slab) * kVK + tid] = ssum;
+}
+
+// one CTA per cloud: combine slabs, subtract S*W2, intra-normalise per cluster, flatten
+// feature-major ([d*64 + k], backbones.py:258-260), global l2-normalise.
+__global__ void __launch_bounds__(kVD)
+netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restrict__ part_s,
+                        const float* __restrict__ cw2, float* __restrict__ vlad) {
+  __shared__ float s_sum[kVK];
+  __shared__ float s_red[kVD / 32][kVK];
+  __shared__ float s_inv[kVK];
+  __shared__ float s_tot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+
+  if (tid < kVK) {
+    float s = 0.f;
+    for (int c = 0; c < kVSlabs; ++c) s += part_s[((long long)b * kVSlabs + c) * kVK + tid];
+    s_sum[tid] = s;
+  }
+  float v[kVK];
+#pragma unroll
+  for (int k = 0; k < kVK; ++k) v[k] = 0.f;
+  for (int c = 0; c < kVSlabs; ++c) {
+    const float* pv = part_v + (((long long)b * kVSlabs + c) * kVD + tid) * kVK;
+#pragma unroll
+    for (int k = 0; k < kVK; k += 4) {
+      const float4 t = ldg4(pv + k);
+      v[k] += t.x; v[k + 1] += t.y; v[k + 2] += t.z; v[k + 3] += t.w;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kVK; ++k) {
+    v[k] -= s_sum[k] * __ldg(cw2 + tid * kVK + k);
+    const float ss = warp_sum(v[k] * v[k]);
+    if (lane == 0) s_red[warp][k] = ss;
+  }
+  __syncthreads();
+  if (tid < kVK) {
+    float ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < kVD / 32; ++w) ss += s_red[w][tid];
+    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+    s_inv[tid] = inv;
+    s_red[0][tid] = ss * inv * inv;  // squared norm of the normalised cluster column
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int k = 0; k < kVK; ++k) tot += s_red[0][k];
+    s_tot = rsqrtf(fmaxf(tot, 1e-12f));
+  }
+  __syncthreads();
+  const float g = s_tot;
+  float* o = vlad + ((long long)b * kVD + tid) * kVK;
+#pragma unroll
+  for (int k = 0; k < kVK; k += 4)
+    *reinterpret_cast<float4*>(o + k) =
+        make_float4(v[k] * s_inv[k] * g, v[k + 1] * s_inv[k + 1] * g, v[k + 2] * s_inv[k + 2] * g,
+                    v[k + 3] * s_inv[k + 3] * g);
+}
+
+// split-K projection: CTA s handles rows [s*128, s*128+128) of hidden1_weights [16384, 256] for a
+// group of up to 32 clouds; thread = output column.  part_h [slices][B][256].
+__global__ void __launch_bounds__(kVD)
+netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__ hw, int B, int KD,
+                       float* __restrict__ part_h) {
+  __shared__ float s_x[32][kVSlice];
+  const int tid = threadIdx.x;
+  const int slice = blockIdx.x;
+  const int b0 = blockIdx.y * 32;
+  const int nb = min(32, B - b0);
+  for (int i = tid; i < nb * kVSlice; i += kVD) {
+    const int bb = i / kVSlice, r = i % kVSlice;
+    s_x[bb][r] = __ldg(vlad + (long long)(b0 + bb) * KD + (long long)slice * kVSlice + r);
+  }
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
+#pragma unroll 4
+  for (int r = 0; r < kVSlice; ++r) {
+    const float wv = __ldg(w + (long long)r * kVD);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = fmaf(s_x[i][r], wv, acc[i]);
+  }
+  for (int i = 0; i < nb; ++i)
+    part_h[((long long)slice * B + b0 + i) * kVD + tid] = acc[i];
+}
+
+// one CTA per cloud: sum slices -> BN -> context gating (256x256 matvec, BN, sigmoid) -> optional
+// final l2-normalise (core/model.py:205, epsilon 1e-8).
+__global__ void __launch_bounds__(kVD)
+netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B,
+                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                    const float* __restrict__ gw, const float* __restrict__ g_scale,
+                    const float* __restrict__ g_shift, int final_l2norm, float* __restrict__ out) {
+  __shared__ float s_h[kVD];
+  __shared__ float s_red[kVD / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  float h = 0.f;
+  for (int s = 0; s < slices; ++s) h += part_h[((long long)s * B + b) * kVD + tid];
+  h = fmaf(h, __ldg(bn_scale + tid), __ldg(bn_shift + tid));
+  s_h[tid] = h;
+  __syncthreads();
+  float g = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < kVD; ++i) g = fmaf(s_h[i], __ldg(gw + i * kVD + tid), g);
+  g = fmaf(g, __ldg(g_scale + tid), __ldg(g_shift + tid));
+  float y = h * (1.f / (1.f + __expf(-g)));
+  if (final_l2norm) {
+    const float ss = warp_sum(y * y);
+    if (lane == 0) s_red[warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kVD / 32; ++w) tot += s_red[w];
+    y *= rsqrtf(fmaxf(tot, 1e-8f));
+  }
+  out[(long long)b * kVD + tid] = y;
+}
+
+static size_t nv_part_v_bytes(int B) { return align_up((size_t)B * kVSlabs * kVD * kVK * 4, 256); }
+static size_t nv_part_s_bytes(int B) { return align_up((size_t)B * kVSlabs * kVK * 4, 256); }
+static size_t nv_vlad_bytes(int B) { return align_up((size_t)B * kVD * kVK * 4, 256); }
+static size_t nv_part_h_bytes(int B) {
+  return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
+}
+
+size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
+  (void)N;
+  if (B <= 0 || D != kVD || Kc != kVK || out_dim != kVD) return 0;
+  return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_part_h_bytes(B);
+}
+
+int netvlad_launch(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
+                   const float* cw, const float* cbn_scale, const float* cbn_shift, const float* cw2,
+                   const float* hw, const float* bn_scale, const float* bn_shift, const float* gw,
+                   const float* gbn_scale, const float* gbn_shift, int final_l2norm, float* out,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!features || !att || !cw || !cbn_scale || !cbn_shift || !cw2 || !hw || !bn_scale || !bn_shift ||
+      !gw || !gbn_scale || !gbn_shift || !out)
+    return DH3D_ERR_NULL;
+  if (B <= 0 || N <= 0) return DH3D_ERR_DIM;
+  if (D != kVD || Kc != kVK || out_dim != kVD || B > 65535) return DH3D_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < netvlad_workspace_bytes(B, N, D, Kc, out_dim)) return DH3D_ERR_WORKSPACE;
+  if ((((uintptr_t)features | (uintptr_t)ws | (uintptr_t)cw | (uintptr_t)cbn_scale |
+        (uintptr_t)cbn_shift) & 15) != 0)
+    return DH3D_ERR_ALIGN;
+  char* p = reinterpret_cast<char*>(ws);
+  float* part_v = reinterpret_cast<float*>(p); p += nv_part_v_bytes(B);
+  float* part_s = reinterpret_cast<float*>(p); p += nv_part_s_bytes(B);
+  float* vlad = reinterpret_cast<float*>(p); p += nv_vlad_bytes(B);
+  float* part_h = reinterpret_cast<float*>(p);
+
+  cudaError_t e = cudaFuncSetAttribute(netvlad_aggregate_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(VladSmem));
+  if (e != cudaSuccess) return (int)e;
+  netvlad_aggregate_kernel<<<dim3(kVSlabs, B), kVD, sizeof(VladSmem), st>>>(
+      features, att, N, cw, cbn_scale, cbn_shift, part_v, part_s);
+  int rc = launch_status();
+  if (rc != DH3D_OK) return rc;
+  netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, cw2, vlad);
+  if ((rc = launch_status()) != DH3D_OK) return rc;
+  const int slices = kVD * kVK / kVSlice;
+  netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
+  if ((rc = launch_status()) != DH3D_OK) return rc;
+  netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, bn_scale, bn_shift, gw, gbn_scale,
+                                        gbn_shift, final_l2norm, out);
+  return launch_status();
+}
+
+}  // namespace dh3d

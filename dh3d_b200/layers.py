@@ -1,0 +1,178 @@
+"""Layer-level API (boundary C): the parameter-owning layers ``core/model.py`` builds on.
+
+Mirrors ``core/layers.py`` of the reference (Keras ``Layer`` classes + function forms) as
+``torch.nn.Module``s whose parameters carry the reference's variable names and shapes, so a
+name-mapped loader can fill them from the shipped TF checkpoints:
+
+    KnnBruteforce / knn_bruteforce            core/layers.py:49-107   (returns [B,K,N] like the layer)
+    FlexPooling / flex_pooling                :110-175
+    FlexConvolution / flex_convolution        :178-339, 439-461   position_theta [3,Din,Dout],
+                                              position_bias [Din,Dout], feature_bias [Dout,1]
+    Flex_Avg / flex_avg                       :342-436, 464-480   theta = 0, bias = I
+    ConvolutionPointset / convolution_pointset :564-707           position_theta [Din,Dout], position_bias [Dout]
+
+``forward`` takes the reference's channel-major tensors ([B,C,N], [B,K,N]); ``forward_pm`` is the
+native point-major fast path the assembled forward pass uses (with the follow-up BatchNorm and
+activation fused into the kernel epilogue).  Inference only.
+"""
+import torch
+from torch import nn
+
+from . import ops, user_ops
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+TENSORPACK_BN_EPS = 1e-5  # tensorpack BatchNorm default epsilon (library default; parity unpinned)
+SLIM_BN_EPS = 1e-3        # tf.contrib slim / layers batch_norm default epsilon
+
+
+class BatchNorm(nn.Module):
+    """Inference BatchNorm statistics.  tensorpack names: gamma, beta, mean/EMA, variance/EMA;
+    slim names: gamma, beta, moving_mean, moving_variance -- both map to these four tensors."""
+
+    def __init__(self, channels, eps=TENSORPACK_BN_EPS):
+        super().__init__()
+        self.eps = eps
+        self.gamma = nn.Parameter(torch.ones(channels), requires_grad=False)
+        self.beta = nn.Parameter(torch.zeros(channels), requires_grad=False)
+        self.mean_ema = nn.Parameter(torch.zeros(channels), requires_grad=False)
+        self.variance_ema = nn.Parameter(torch.ones(channels), requires_grad=False)
+
+    def fold(self, pre_bias=None):
+        """(scale, shift) with y = x*scale + shift == BN(x + pre_bias)."""
+        scale = self.gamma / torch.sqrt(self.variance_ema + self.eps)
+        bias = 0.0 if pre_bias is None else pre_bias.reshape(-1)
+        shift = (bias - self.mean_ema) * scale + self.beta
+        return scale.contiguous(), shift.contiguous()
+
+
+def invalidate_folded(module):
+    """Drop every cached folded-BN tensor (call after changing parameters)."""
+    for m in module.modules():
+        if hasattr(m, "_folded"):
+            m._folded = None
+
+
+class KnnBruteforce(nn.Module):
+    def __init__(self, k, data_format="simple"):
+        super().__init__()
+        assert k > 0 and data_format == "simple"
+        self.k = k
+
+    def forward(self, positions):
+        """positions [B,Dp,N] -> (NN [B,K,N] i32, distances [B,K,N])  (core/layers.py:85-98)."""
+        nn_, dist = user_ops.knn_bruteforce(positions, self.k)
+        return ops.transpose_pm_to_cm(nn_), ops.transpose_pm_to_cm(dist)
+
+
+def knn_bruteforce(positions, k, data_format="simple", name=None):
+    return KnnBruteforce(k, data_format)(positions)
+
+
+class FlexPooling(nn.Module):
+    def forward(self, features, neighborhoods):
+        return user_ops.flex_pooling(features, neighborhoods)[0]
+
+    def forward_pm(self, features, neighborhoods):
+        return ops.flex_pool(features, neighborhoods)
+
+
+def flex_pooling(features, neighborhoods, data_format="simple", name=None):
+    return FlexPooling()(features, neighborhoods)
+
+
+class FlexConvolution(nn.Module):
+    def __init__(self, in_channels, filters, use_feature_bias=True, dp=3):
+        super().__init__()
+        self.filters = int(filters)
+        self.position_theta = nn.Parameter(torch.zeros(dp, in_channels, filters), requires_grad=False)
+        self.position_bias = nn.Parameter(torch.zeros(in_channels, filters), requires_grad=False)
+        self.feature_bias = (nn.Parameter(torch.zeros(filters, 1), requires_grad=False)
+                             if use_feature_bias else None)
+        self._folded = None
+
+    def forward(self, features, positions, neighborhoods):
+        y = user_ops.flex_convolution(features, positions, neighborhoods, self.position_theta,
+                                      self.position_bias)
+        if self.feature_bias is not None:
+            y = y + self.feature_bias  # [Dout,1] broadcast over [B,Dout,N]  (core/layers.py:330-331)
+        return y
+
+    def forward_pm(self, features, xyz, neighborhoods, bn=None, act=ACT_NONE):
+        if self._folded is None:  # folded once; call invalidate_folded(model) after loading weights
+            scale = shift = None
+            if bn is not None:
+                scale, shift = bn.fold()
+            fb = None if self.feature_bias is None else self.feature_bias.reshape(-1).contiguous()
+            self._folded = (fb, scale, shift)
+        fb, scale, shift = self._folded
+        return ops.flex_conv(features, self.position_theta, self.position_bias, neighborhoods, xyz,
+                             feature_bias=fb, scale=scale, shift=shift, act=act)
+
+
+def flex_convolution(layer, features, positions, neighborhoods):
+    return layer(features, positions, neighborhoods)
+
+
+class Flex_Avg(FlexConvolution):
+    """FlexConv with theta = 0 and bias = I: the plain neighbour SUM (caller scales by 1/K,
+    core/backbones.py:80-83).  Requires Din == Dout."""
+
+    def __init__(self, channels):
+        super().__init__(channels, channels, use_feature_bias=False)
+        with torch.no_grad():
+            self.position_bias.copy_(torch.eye(channels))
+
+
+class ConvolutionPointset(nn.Module):
+    def __init__(self, in_channels, filters, use_feature_bias=False):
+        super().__init__()
+        self.filters = int(filters)
+        self.position_theta = nn.Parameter(torch.zeros(in_channels, filters), requires_grad=False)
+        self.position_bias = nn.Parameter(torch.zeros(filters), requires_grad=False)
+        self.feature_bias = (nn.Parameter(torch.zeros(filters, 1), requires_grad=False)
+                             if use_feature_bias else None)
+        self._folded = None
+
+    def forward(self, features, neighborhoods):
+        y = user_ops.convolution_pointset(features, neighborhoods, self.position_theta,
+                                          self.position_bias)
+        if self.feature_bias is not None:
+            y = y + self.feature_bias
+        return y
+
+    def forward_pm(self, features, neighborhoods, bn=None, act=ACT_NONE):
+        if self._folded is None:
+            scale = shift = None
+            if bn is not None:
+                scale, shift = bn.fold(None if self.feature_bias is None else self.feature_bias)
+            self._folded = (scale, shift)
+        scale, shift = self._folded
+        return ops.conv_pointset(features, self.position_theta, self.position_bias, neighborhoods,
+                                 scale=scale, shift=shift, act=act)
+
+
+class Conv1x1(nn.Module):
+    """tensorpack ``Conv2D(kernel_shape=1)`` on [B,N,1,C] (core/tf_utils.py:99-109): W [1,1,Cin,Cout],
+    b [Cout], optional BatchNorm ('bn' scope) and activation.  Point-major only."""
+
+    def __init__(self, in_channels, out_channels, bn=True, act=ACT_RELU):
+        super().__init__()
+        self.W = nn.Parameter(torch.zeros(1, 1, in_channels, out_channels), requires_grad=False)
+        self.b = nn.Parameter(torch.zeros(out_channels), requires_grad=False)
+        self.bn = BatchNorm(out_channels) if bn else None
+        self.act = act
+        self._folded = None
+
+    def folded(self):
+        if self._folded is None:
+            w = self.W.reshape(self.W.shape[2], self.W.shape[3]).contiguous()
+            if self.bn is not None:
+                scale, shift = self.bn.fold(self.b)
+            else:
+                scale, shift = None, self.b.detach().contiguous()
+            self._folded = (w, scale, shift)
+        return self._folded
+
+    def forward(self, x, out=None, out_col=0):
+        w, scale, shift = self.folded()
+        return ops.linear(x, w, scale=scale, shift=shift, act=self.act, out=out, out_col=out_col)

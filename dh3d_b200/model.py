@@ -1,0 +1,120 @@
+"""DH3D forward pass (inference branch of ``DH3D.build_graph``, reference core/model.py:135-206).
+
+    points [B,N,3] -> knn (model.py:157) -> backbone_local_dilate (:99-108) -> l2-normalised local
+    descriptors 'xyz_feat' (:177-181) -> detection_block attention 'xyz_feat_att' (:184-188) ->
+    compute_global (:112-133): global_before_assemble -> globalatt -> attention NetVLAD ->
+    l2-normalised 'globaldesc' (:203-205).
+
+Every tensor op below is a launch of this repo's own CUDA kernels through the C ABI; torch only
+allocates buffers and sequences streams.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from .backbones import (DetectionBlock, DilateGeometry, FlexConvDilate, GlobalAttBlock,
+                        GlobalNetVLADBlock, LocalBackbone)
+from .configs import DH3DConfig
+from .layers import invalidate_folded
+
+
+class DH3D(nn.Module):
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = config or DH3DConfig()
+        c = self.config
+        self.local = LocalBackbone(c.init_feat_dim, c.featdim, dilate2=c.dilate, knn=c.knn_num)
+        if c.detection:
+            self.detection_block_reliable = DetectionBlock(c.featdim)
+        if c.extract_global:
+            assert list(c.gl_dims) == [256], "only the shipped gl_dims=[256] configuration is built"
+            self.global_before_assemble = FlexConvDilate(c.featdim, c.gl_dims, dilate=c.gl_dilate,
+                                                         knn=c.knn_num, concat=False, add_se="")
+            self.globalatt = GlobalAttBlock(c.gl_dims[-1])
+            self.netvlad = GlobalNetVLADBlock(c.gl_dims[-1], c.cluster_size, c.output_dim)
+        self._side = None
+
+    def invalidate(self):
+        invalidate_folded(self)
+
+    @torch.no_grad()
+    def forward(self, points, knn_inds=None, outputs=("local_desc", "attention", "globaldesc"),
+                overlap=True):
+        """points [B,N,3] fp32 CUDA; knn_inds optional [B,N,K] i32 (the reference's 'knn_inds'
+        input for N > 8192, model.py:148-155).  Returns a dict with the requested tensors:
+          feat [B,N,128] raw, local_desc [B,N,128] l2-normed, attention [B,N,1], globaldesc [B,256],
+          xyz_feat [B,N,131], xyz_feat_att [B,N,132] (the reference's saved tensor names)."""
+        c = self.config
+        points = points.contiguous()
+        out = {}
+        same_geometry = c.extract_global and c.gl_dilate == c.dilate
+        cur = torch.cuda.current_stream(points.device)
+
+        # xyz-only geometry (FPS chain is latency-bound and independent of stage 1): side stream
+        geometry = None
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=points.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
+        if knn_inds is None:
+            knn_inds, _ = ops.knn_points(points, c.knn_num)
+        if overlap:
+            cur.wait_stream(self._side)
+            for t in (geometry.kp_indices, geometry.points_sampled, geometry.knn_indices,
+                      geometry.nn_dist, geometry.nn_idx):
+                t.record_stream(cur)
+        else:
+            geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
+
+        feat = self.local(points, knn_inds, geometry=geometry)
+        out["feat"] = feat
+        want = set(outputs)
+        if want & {"local_desc", "xyz_feat", "xyz_feat_att"}:
+            out["local_desc"] = ops.l2_normalize_rows(feat, 1e-8)
+        if c.detection and want & {"attention", "xyz_feat_att"}:
+            out["attention"] = self.detection_block_reliable(feat)
+        if c.extract_global and "globaldesc" in want:
+            g = geometry if same_geometry else None
+            forglobal = self.global_before_assemble(points, feat, geometry=g)
+            att = self.globalatt(forglobal)
+            out["globaldesc"] = self.netvlad(points, forglobal, att, final_l2norm=True)
+        if "xyz_feat" in want:
+            out["xyz_feat"] = torch.cat([points, out["local_desc"]], dim=-1)
+        if "xyz_feat_att" in want and c.detection:
+            out["xyz_feat_att"] = torch.cat([points, out["local_desc"], out["attention"]], dim=-1)
+        return out
+
+
+def init_random_(model, seed=0, knn=8, offset_scale=2.0):
+    """Random-init weights of the right shapes (benchmarks have no network for checkpoints), scaled
+    so activations stay O(1) through the stack for clouds whose neighbour offsets are about
+    ``offset_scale`` metres: FlexConv weights w = bias + theta.delta get var 1/(K*Din), 1x1 kernels
+    N(0, 1/fan_in), BN statistics near identity.  Deterministic per seed."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            shape = tuple(p.shape)
+            leaf = name.split(".")[-1]
+            r = lambda: torch.randn(shape, generator=g)
+            if leaf == "gamma":
+                v = 1.0 + 0.1 * r()
+            elif leaf == "variance_ema":
+                v = 1.0 + 0.2 * torch.rand(shape, generator=g)
+            elif leaf in ("beta", "mean_ema", "b", "feature_bias"):
+                v = 0.1 * r()
+            elif leaf == "position_theta" and len(shape) == 3:      # FlexConv [3,Din,Dout]
+                v = r() * (0.5 / (knn * shape[1])) ** 0.5 / offset_scale
+            elif leaf == "position_bias" and len(shape) == 2:       # FlexConv [Din,Dout]
+                v = r() * (0.5 / (knn * shape[0])) ** 0.5
+            elif leaf == "position_theta":                          # ConvPointset [Din,Dout]
+                v = r() * (1.0 / (knn * shape[0])) ** 0.5 / offset_scale
+            elif leaf == "position_bias":                           # ConvPointset [Dout]
+                v = 0.1 * r()
+            else:
+                fan_in = shape[-2] if len(shape) >= 2 else shape[0]
+                v = r() / (float(fan_in) ** 0.5)
+            p.copy_(v.to(p.dtype))
+    model.invalidate()
+    return model

@@ -1,0 +1,245 @@
+"""Native (point-major) operator layer: thin torch-tensor wrappers over the C ABI.
+
+Layouts here are the library's native ones -- features [B,N,C], neighbourhoods [B,N,K], xyz
+[B,N,3] -- and every op can fuse the reference's follow-up BatchNorm/bias/activation.  The
+reference-signature (channel-major) mirrors live in ``dh3d_b200.user_ops`` / ``dh3d_b200.tf_ops``.
+Outputs are allocated here with torch (the reference: TF's ``allocate_output``).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, call, check, opt, query, stream_ptr, workspace
+
+f32, i32 = torch.float32, torch.int32
+_ci, _cf, _cs = ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+def knn_points(xyz, k):
+    """xyz [B,N,3] -> (ids [B,N,K] i32, dists [B,N,K] f32).  Reference order and ties, see knn.cu."""
+    px = check(xyz, f32, "xyz", 3)
+    B, N, D = xyz.shape
+    if D != 3:
+        raise _lib.Dh3dError("knn_points: last dim must be 3")
+    ids = torch.empty((B, N, k), dtype=i32, device=xyz.device)
+    dists = torch.empty((B, N, k), dtype=f32, device=xyz.device)
+    ws, wp, wn = workspace(query("dh3d_knn_workspace_bytes", B, N), xyz.device)
+    call("dh3d_knn_bruteforce_pm", px, B, N, int(k), check(ids, i32, "ids"), check(dists, f32, "dists"),
+         wp, wn, stream_ptr(xyz.device))
+    return ids, dists
+
+
+def flex_conv(features, theta, bias, neighborhood, xyz, feature_bias=None, scale=None, shift=None,
+              act=ACT_NONE):
+    """features [B,N,Din], theta [3,Din,Dout], bias [Din,Dout], neighborhood [B,N,K] i32,
+    xyz [B,N,3] -> act((flexconv + feature_bias) * scale + shift)  [B,N,Dout]."""
+    B, N, Din = features.shape
+    K = neighborhood.shape[2]
+    Dout = theta.shape[2]
+    if tuple(theta.shape) != (3, Din, Dout) or tuple(bias.shape) != (Din, Dout):
+        raise _lib.Dh3dError("flex_conv: theta/bias shapes %s %s do not match Din=%d" %
+                             (tuple(theta.shape), tuple(bias.shape), Din))
+    if tuple(neighborhood.shape[:2]) != (B, N) or tuple(xyz.shape) != (B, N, 3):
+        raise _lib.Dh3dError("flex_conv: neighborhood/xyz shape mismatch")
+    out = torch.empty((B, N, Dout), dtype=f32, device=features.device)
+    ws, wp, wn = workspace(query("dh3d_flex_conv_pm_workspace_bytes", B, N, K, Din, Dout),
+                           features.device)
+    call("dh3d_flex_conv_pm", check(features, f32, "features"), check(theta, f32, "theta"),
+         check(bias, f32, "bias"), check(neighborhood, i32, "neighborhood"), check(xyz, f32, "xyz"),
+         check(out, f32, "out"), B, N, K, Din, Dout, opt(feature_bias, f32, "feature_bias"),
+         opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act), wp, wn,
+         stream_ptr(features.device))
+    return out
+
+
+def flex_pool(features, neighborhood, with_argmax=False):
+    B, N, D = features.shape
+    K = neighborhood.shape[2]
+    out = torch.empty_like(features)
+    arg = torch.empty((B, N, D), dtype=i32, device=features.device) if with_argmax else None
+    call("dh3d_flex_pool_pm", check(features, f32, "features", 3),
+         check(neighborhood, i32, "neighborhood", 3), check(out, f32, "out"), opt(arg, i32, "argmax"),
+         B, N, K, D, stream_ptr(features.device))
+    return (out, arg) if with_argmax else out
+
+
+def conv_pointset(features, theta, bias, neighborhood, scale=None, shift=None, act=ACT_NONE):
+    B, N, Din = features.shape
+    K = neighborhood.shape[2]
+    Dout = theta.shape[1]
+    if tuple(theta.shape) != (Din, Dout) or tuple(bias.shape) != (Dout,):
+        raise _lib.Dh3dError("conv_pointset: theta/bias shape mismatch")
+    out = torch.empty((B, N, Dout), dtype=f32, device=features.device)
+    call("dh3d_conv_pointset_pm", check(features, f32, "features", 3), check(theta, f32, "theta"),
+         check(bias, f32, "bias"), check(neighborhood, i32, "neighborhood", 3), check(out, f32, "out"),
+         B, N, K, Din, Dout, opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act),
+         stream_ptr(features.device))
+    return out
+
+
+def farthest_point_sample(npoint, inp):
+    B, N, _ = inp.shape
+    out = torch.empty((B, npoint), dtype=i32, device=inp.device)
+    call("dh3d_farthest_point_sample", B, N, int(npoint), check(inp, f32, "inp", 3),
+         check(out, i32, "out"), stream_ptr(inp.device))
+    return out
+
+
+def gather_point(inp, idx):
+    B, N, _ = inp.shape
+    M = idx.shape[1]
+    out = torch.empty((B, M, 3), dtype=f32, device=inp.device)
+    call("dh3d_gather_point", B, N, M, check(inp, f32, "inp", 3), check(idx, i32, "idx", 2),
+         check(out, f32, "out"), stream_ptr(inp.device))
+    return out
+
+
+def group_point(points, idx):
+    B, N, C = points.shape
+    _, M, S = idx.shape
+    out = torch.empty((B, M, S, C), dtype=f32, device=points.device)
+    call("dh3d_group_point", B, N, C, M, S, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
+         check(out, f32, "out"), stream_ptr(points.device))
+    return out
+
+
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = torch.empty((B, m, nsample), dtype=i32, device=xyz1.device)
+    cnt = torch.empty((B, m), dtype=i32, device=xyz1.device)
+    ws, wp, wn = workspace(query("dh3d_query_ball_point_workspace_bytes", B, m), xyz1.device)
+    call("dh3d_query_ball_point", B, n, m, _cf(radius), int(nsample), check(xyz1, f32, "xyz1", 3),
+         check(xyz2, f32, "xyz2", 3), check(idx, i32, "idx"), check(cnt, i32, "cnt"), wp, wn,
+         stream_ptr(xyz1.device))
+    return idx, cnt
+
+
+def three_nn(xyz1, xyz2):
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = torch.empty((B, n, 3), dtype=f32, device=xyz1.device)
+    idx = torch.empty((B, n, 3), dtype=i32, device=xyz1.device)
+    call("dh3d_three_nn", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
+         check(dist, f32, "dist"), check(idx, i32, "idx"), stream_ptr(xyz1.device))
+    return dist, idx
+
+
+def three_interpolate(points, idx, weight, weight_is_dist2=False):
+    B, m, c = points.shape
+    n = idx.shape[1]
+    out = torch.empty((B, n, c), dtype=f32, device=points.device)
+    name = "dh3d_three_interpolate_from_dist" if weight_is_dist2 else "dh3d_three_interpolate"
+    call(name, B, m, c, n, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
+         check(weight, f32, "weight", 3), check(out, f32, "out"), stream_ptr(points.device))
+    return out
+
+
+def _rows(x):
+    """[..., C] contiguous tensor -> (M, C) row view parameters."""
+    C = x.shape[-1]
+    return x.numel() // C, C
+
+
+def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0):
+    """act((x @ w) * scale + shift) over the last dim of x.  ``out``/``out_col`` write the result
+    into columns [out_col, out_col+N) of an existing [..., ldy] tensor (fused concat)."""
+    M, K = _rows(x)
+    N = w.shape[1]
+    if w.shape[0] != K:
+        raise _lib.Dh3dError("linear: x has %d columns, w has %d rows" % (K, w.shape[0]))
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=f32, device=x.device)
+        ldy, yptr = N, check(out, f32, "out")
+    else:
+        check(out, f32, "out")
+        ldy = out.shape[-1]
+        yptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col)
+    call("dh3d_linear", check(x, f32, "x"), K, check(w, f32, "w", 2), opt(scale, f32, "scale"),
+         opt(shift, f32, "shift"), int(act), yptr, ldy, M, K, N, stream_ptr(x.device))
+    return out
+
+
+def rowdot(x, w, bias=0.0, act=ACT_NONE):
+    M, K = _rows(x)
+    y = torch.empty(x.shape[:-1], dtype=f32, device=x.device)
+    call("dh3d_rowdot", check(x, f32, "x"), K, check(w, f32, "w"), _cf(float(bias)), int(act),
+         check(y, f32, "y"), M, K, stream_ptr(x.device))
+    return y
+
+
+def se_excite(x, gate):
+    y = torch.empty_like(x)
+    call("dh3d_se_excite", check(x, f32, "x"), check(gate, f32, "gate"), check(y, f32, "y"),
+         _cs(x.numel()), stream_ptr(x.device))
+    return y
+
+
+def add(a, b):
+    y = torch.empty_like(a)
+    call("dh3d_add", check(a, f32, "a"), check(b, f32, "b"), check(y, f32, "y"), _cs(a.numel()),
+         stream_ptr(a.device))
+    return y
+
+
+def l2_normalize_rows(x, eps, out=None, out_col=0):
+    M, C = _rows(x)
+    if out is None:
+        out = torch.empty_like(x)
+        ldy, yptr = C, check(out, f32, "out")
+    else:
+        check(out, f32, "out")
+        ldy = out.shape[-1]
+        yptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col)
+    call("dh3d_l2_normalize_rows", check(x, f32, "x"), C, yptr, ldy, M, C, _cf(eps),
+         stream_ptr(x.device))
+    return out
+
+
+def copy_cols(src, dst, dst_col):
+    """dst[..., dst_col:dst_col+C] = src[..., :C]"""
+    M, C = _rows(src)
+    check(dst, f32, "dst")
+    call("dh3d_copy_cols", check(src, f32, "src"), C, ctypes.c_void_p(dst.data_ptr() + 4 * dst_col),
+         dst.shape[-1], M, C, stream_ptr(src.device))
+    return dst
+
+
+def transpose_cm_to_pm(x):
+    """[B,C,N] -> [B,N,C] (fp32 or int32)."""
+    B, C, N = x.shape
+    out = torch.empty((B, N, C), dtype=x.dtype, device=x.device)
+    call("dh3d_transpose_cm_to_pm", check(x, x.dtype, "x", 3), check(out, x.dtype, "out"), B, C, N,
+         stream_ptr(x.device))
+    return out
+
+
+def transpose_pm_to_cm(x):
+    B, N, C = x.shape
+    out = torch.empty((B, C, N), dtype=x.dtype, device=x.device)
+    call("dh3d_transpose_pm_to_cm", check(x, x.dtype, "x", 3), check(out, x.dtype, "out"), B, N, C,
+         stream_ptr(x.device))
+    return out
+
+
+def netvlad(features, att, cluster_weights, cluster_bn, cluster_weights2, hidden1_weights, bn,
+            gating_weights, gating_bn, final_l2norm=True):
+    """features [B,N,D], att [B,N] (or [B,N,1]); *_bn = (scale, shift) folded BatchNorm pairs."""
+    B, N, D = features.shape
+    Kc = cluster_weights.shape[1]
+    out_dim = hidden1_weights.shape[1]
+    att = att.reshape(B, N)
+    out = torch.empty((B, out_dim), dtype=f32, device=features.device)
+    nbytes = query("dh3d_netvlad_workspace_bytes", B, N, D, Kc, out_dim)
+    if nbytes == 0:
+        raise _lib.Dh3dError("netvlad: unsupported configuration D=%d Kc=%d out=%d" % (D, Kc, out_dim))
+    ws, wp, wn = workspace(nbytes, features.device)
+    call("dh3d_netvlad", check(features, f32, "features", 3), check(att, f32, "att"), B, N, D, Kc,
+         out_dim, check(cluster_weights, f32, "cluster_weights"), check(cluster_bn[0], f32, "cbn_s"),
+         check(cluster_bn[1], f32, "cbn_b"), check(cluster_weights2.reshape(D, Kc), f32, "cw2"),
+         check(hidden1_weights, f32, "hidden1_weights"), check(bn[0], f32, "bn_s"),
+         check(bn[1], f32, "bn_b"), check(gating_weights, f32, "gating_weights"),
+         check(gating_bn[0], f32, "gbn_s"), check(gating_bn[1], f32, "gbn_b"), int(bool(final_l2norm)),
+         check(out, f32, "out"), wp, wn, stream_ptr(features.device))
+    return out

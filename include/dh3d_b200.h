@@ -1,0 +1,201 @@
+/*
+ * dh3d_b200.h -- C ABI of libdh3d_b200.so: the DH3D point-cloud feature-extraction hot path
+ * as hand-written sm_100a CUDA.  This is the drop-in boundary: every entry point replaces one
+ * TensorFlow custom op (or one TF-library block) of the reference and takes exactly what the
+ * reference's OpKernel::Compute / *Launcher gets -- raw device pointers, dimensions, a stream.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer to a dense, contiguous fp32 / int32 buffer owned by the
+ *     caller (the reference: `ctx->allocate_output`, e.g. user_ops/kernels/flex_conv_op.cc:47-49);
+ *     inputs are never written; outputs are fully overwritten;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); launches are
+ *     asynchronous, nothing here synchronises (the reference's kNN does a cudaDeviceSynchronize,
+ *     knn_bruteforce_kernel_gpu.cu.cc:222 -- deliberately not inherited);
+ *   - re-entrant, no global mutable state; `workspace` buffers are caller-owned scratch whose
+ *     minimum size comes from the matching *_workspace_bytes() query;
+ *   - return value: DH3D_OK (0), a negative DH3D_ERR_* argument-validation code, or a positive
+ *     cudaError_t from the launch (the reference: TF Status via OP_REQUIRES / errors::Internal,
+ *     flex_conv_kernel_gpu.cu.cc:436-439);
+ *   - layouts: "cm" = channel-major [B,C,N] (the reference's user_ops layout), "pm" = point-major
+ *     [B,N,C] (the reference's tf_ops layout and this library's native layout).
+ */
+#ifndef DH3D_B200_H_
+#define DH3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DH3D_API __attribute__((visibility("default")))
+#else
+#define DH3D_API
+#endif
+
+#define DH3D_OK 0
+#define DH3D_ERR_NULL (-1)        /* a required pointer is NULL */
+#define DH3D_ERR_DIM (-2)         /* a dimension is <= 0 or inconsistent */
+#define DH3D_ERR_UNSUPPORTED (-3) /* size / attribute outside what the kernels support */
+#define DH3D_ERR_WORKSPACE (-4)   /* workspace missing or too small */
+#define DH3D_ERR_ALIGN (-5)       /* pointer not aligned for vector access (16 bytes) */
+
+#define DH3D_ACT_NONE 0
+#define DH3D_ACT_RELU 1
+#define DH3D_ACT_SIGMOID 2
+
+DH3D_API int dh3d_version(void);                 /* 100 * major + minor */
+DH3D_API const char* dh3d_error_string(int code); /* static string for a DH3D_ERR_* / cudaError_t code */
+
+/* ---------------------------------------------------------------------------------------------
+ * k-NN  -- replaces op KnnBruteforce
+ *   reference: user_ops/ops/knn_bruteforce.cc:11-35 (schema), kernels/knn_bruteforce_op.cc:30-60,
+ *   kernels/knn_bruteforce_kernel_gpu.cu.cc:45-134,162-228; python user_ops/__init__.py:50.
+ *   positions [B,3,N] cm (or [B,N,3] pm for the _pm entry) -> ids [B,N,K] i32 (self included,
+ *   ascending Euclidean distance, ties in the reference's BlockRadixSort blocked order), dists
+ *   [B,N,K] f32 (sqrt'ed).  K in [1,32]; N in [1, 65536]; Dp must be 3 (the only value DH3D uses).
+ *   Unlike the reference there is no N <= 8192 cap (kernel_gpu.cu.cc:213-221); for N > 8192 the
+ *   tie order is plain index order.
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API size_t dh3d_knn_workspace_bytes(int B, int N);
+DH3D_API int dh3d_knn_bruteforce(const float* positions_cm, int B, int Dp, int N, int K, int32_t* ids,
+                        float* dists, void* workspace, size_t workspace_bytes, void* stream);
+DH3D_API int dh3d_knn_bruteforce_pm(const float* xyz_pm, int B, int N, int K, int32_t* ids, float* dists,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FlexConv forward -- replaces op FlexConv
+ *   reference: user_ops/ops/flex_conv.cc:25-100, kernels/flex_conv_op.cc:35-53,
+ *   kernels/flex_conv_kernel_gpu.cu.cc:44-158,402-441; python user_ops/__init__.py:63-89
+ *   (note the op's input order features, theta, bias, neighborhood, position).
+ *   out[b,o,n] = sum_k sum_c (bias[c,o] + sum_dp theta[dp,c,o]*(p[nbr_k]-p[n])[dp]) * f[c,nbr_k]
+ *   Centre = p[n] (the CUDA kernel's rule, :75-79,109).
+ *
+ *   dh3d_flex_conv: reference layouts -- features [B,Din,N], theta [3,Din,Dout], bias [Din,Dout],
+ *   neighborhood [B,K,N] i32, positions [B,3,N] -> out [B,Dout,N].
+ *   dh3d_flex_conv_pm: native layouts -- features [B,N,Din], neighborhood [B,N,K], xyz [B,N,3]
+ *   -> out [B,N,Dout] with an optional fused epilogue
+ *       y = act( (x + feature_bias[o]) * scale[o] + shift[o] )
+ *   (feature_bias: core/layers.py:330-331; scale/shift: folded inference BatchNorm,
+ *   core/tf_utils.py:58-63).  Any of feature_bias/scale/shift may be NULL.
+ *   Din % 4 == 0, Dout % 4 == 0, K in [1,64].
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API size_t dh3d_flex_conv_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_conv(const float* features_cm, const float* theta, const float* bias,
+                   const int32_t* neighborhood_cm, const float* positions_cm, float* out_cm, int B,
+                   int N, int K, int Din, int Dout, void* workspace, size_t workspace_bytes,
+                   void* stream);
+DH3D_API size_t dh3d_flex_conv_pm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_conv_pm(const float* features_pm, const float* theta, const float* bias,
+                      const int32_t* neighborhood_pm, const float* xyz_pm, float* out_pm, int B,
+                      int N, int K, int Din, int Dout, const float* feature_bias,
+                      const float* scale, const float* shift, int act, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FlexPool forward -- replaces op FlexPool
+ *   reference: user_ops/ops/flex_pool.cc:25-69, kernels/flex_pool_kernel_gpu.cu.cc:30-63,100-125;
+ *   python user_ops/__init__.py:115-135.  max over the K neighbours per channel; argmax is the
+ *   GLOBAL point id; first neighbour reaching the max wins.  argmax may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_flex_pool(const float* features_cm, const int32_t* neighborhood_cm, float* out_cm,
+                   int32_t* argmax_cm, int B, int N, int K, int D, void* stream);
+DH3D_API int dh3d_flex_pool_pm(const float* features_pm, const int32_t* neighborhood_pm, float* out_pm,
+                      int32_t* argmax_pm, int B, int N, int K, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ConvPointset forward ("conv_relative") -- replaces op ConvPointset
+ *   reference: user_ops/ops/conv_pointset.cc:26-87, kernels/conv_pointset_kernel_gpu.cu.cc:45-147,
+ *   364-402; python user_ops/__init__.py:205-225.
+ *   out[b,o,n] = bias[o] + sum_k sum_c theta[c,o]*(f[c,nbr_k]-f[c,nbr_0]);  theta [Din,Dout].
+ *   Din <= 64 (one Din chunk of the reference kernel; DH3D uses Din = 3).  The _pm entry has the
+ *   same optional epilogue as dh3d_flex_conv_pm (scale/shift/act).
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_conv_pointset(const float* features_cm, const float* theta, const float* bias,
+                       const int32_t* neighborhood_cm, float* out_cm, int B, int N, int K, int Din,
+                       int Dout, void* stream);
+DH3D_API int dh3d_conv_pointset_pm(const float* features_pm, const float* theta, const float* bias,
+                          const int32_t* neighborhood_pm, float* out_pm, int B, int N, int K,
+                          int Din, int Dout, const float* scale, const float* shift, int act,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PointNet++ ops -- replace the raw-pointer launchers of tf_ops (already a C-like layer there)
+ *   farthestpointsamplingLauncher(b,n,m,inp,temp,out)   tf_ops/sampling/tf_sampling_g.cu:105-170,203
+ *   gatherpointLauncher(b,n,m,inp,idx,out)              tf_sampling_g.cu:172-181,206
+ *   groupPointLauncher(b,n,c,m,nsample,points,idx,out)  tf_ops/grouping/tf_grouping_g.cu:94-111,191
+ *   queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt) tf_grouping_g.cu:3-52,179
+ *   threenn_cpu / threeinterpolate_cpu                  tf_ops/interpolation/tf_interpolate.cpp:60-127
+ *   All point-major.  FPS needs no `temp` scratch (state lives in registers / shared memory).
+ *   FPS: n <= 65536; the sample order reproduces the reference's 512-thread tie rule.
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_farthest_point_sample(int b, int n, int m, const float* inp, int32_t* out, void* stream);
+DH3D_API int dh3d_gather_point(int b, int n, int m, const float* inp, const int32_t* idx, float* out,
+                      void* stream);
+DH3D_API int dh3d_group_point(int b, int n, int c, int m, int nsample, const float* points,
+                     const int32_t* idx, float* out, void* stream);
+DH3D_API size_t dh3d_query_ball_point_workspace_bytes(int b, int m);
+DH3D_API int dh3d_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                          const float* xyz2, int32_t* idx, int32_t* pts_cnt, void* workspace,
+                          size_t workspace_bytes, void* stream);
+DH3D_API int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                  int32_t* idx, void* stream);
+DH3D_API int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                           const float* weight, float* out, void* stream);
+/* fused caller-side step of core/backbones.py:91-96: weight = (1/max(d,1e-10))/sum(...) computed
+ * in-kernel from the squared distances of dh3d_three_nn, then interpolated. */
+DH3D_API int dh3d_three_interpolate_from_dist(int b, int m, int c, int n, const float* points,
+                                     const int32_t* idx, const float* dist2, float* out,
+                                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense 1x1 layers (tensorpack Conv2D kernel_shape=1 + BatchNorm + activation on [B,N,1,C];
+ * call sites core/tf_utils.py:99-109, core/backbones.py:132-173)
+ *   y[m, :] = act( (x[m, :] @ W[K,N]) * scale[:] + shift[:] )      x [M,K] row-major, ldx >= K
+ *   scale NULL -> 1, shift NULL -> 0 (conv bias and folded BN are both carried by scale/shift).
+ *   K % 4 == 0, N % 4 == 0, ldx % 4 == 0, ldy % 4 == 0.
+ * dh3d_rowdot: y[m] = act( sum_k x[m,k]*w[k] + bias )  -- the final 1024->1 / sigmoid layers.
+ * dh3d_se_excite: y = relu(x + x*gate)  (core/backbones.py:45-55, se_res_bottleneck).
+ * dh3d_l2_normalize_rows: y = x / sqrt(max(sum x^2, eps))  (tf.nn.l2_normalize, model.py:177,205)
+ * dh3d_add: y = a + b   (residual join, backbones.py:123)
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, const float* shift,
+                int act, float* y, int ldy, int M, int K, int N, void* stream);
+DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
+                int K, void* stream);
+DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);
+DH3D_API int dh3d_l2_normalize_rows(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
+                           void* stream);
+DH3D_API int dh3d_add(const float* a, const float* b, float* y, size_t count, void* stream);
+/* strided 2-D copy: dst[m, 0:C] = src[m, 0:C] (concat / slice helper; C % 4 == 0, lds % 4 == 0) */
+DH3D_API int dh3d_copy_cols(const float* src, int lds, float* dst, int ldd, int M, int C, void* stream);
+/* [B,C,N] <-> [B,N,C] for fp32 / int32 payloads (bit copies) */
+DH3D_API int dh3d_transpose_cm_to_pm(const void* src_cm, void* dst_pm, int B, int C, int N, void* stream);
+DH3D_API int dh3d_transpose_pm_to_cm(const void* src_pm, void* dst_cm, int B, int N, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention-weighted NetVLAD -- replaces the TF-library graph of
+ *   core/backbones.py:202-279 (global_netvald_block) + :282-320 (context_gating)
+ *   features [B,N,D] pm, att [B,N] -> out [B,out_dim] (pre final l2-normalise; model.py:205 is
+ *   applied when `final_l2norm` != 0, eps 1e-8).
+ *   cluster_weights [D,Kc], cluster_weights2 [D,Kc] (the reference's [1,D,Kc]),
+ *   hidden1_weights [D*Kc, out_dim] (row index d*Kc + k: feature-major, cluster-minor, :258-260),
+ *   gating_weights [out_dim,out_dim]; the three BatchNorms arrive folded to scale/shift:
+ *   cluster_bn (slim, eps 1e-3) [Kc], bn (contrib, eps 1e-3) [out_dim], gating_bn (slim) [out_dim].
+ *   D == 256, Kc == 64, out_dim == 256 (the shipped configuration).
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API size_t dh3d_netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim);
+DH3D_API int dh3d_netvlad(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
+                 const float* cluster_weights, const float* cluster_bn_scale,
+                 const float* cluster_bn_shift, const float* cluster_weights2,
+                 const float* hidden1_weights, const float* bn_scale, const float* bn_shift,
+                 const float* gating_weights, const float* gating_bn_scale,
+                 const float* gating_bn_shift, int final_l2norm, float* out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DH3D_B200_H_ */

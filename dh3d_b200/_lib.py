@@ -52,7 +52,42 @@ _SIGNATURES = {
 }
 
 _lib = None
-launch_count = 0  # C-ABI calls issued through call(); bench.py reports kernels launched from it
+
+# kernels launched per C-ABI call (memcpy/memset nodes not counted); bench.py's gpu_launches claim
+_KERNELS_PER_CALL = {
+    "dh3d_knn_bruteforce": 2, "dh3d_knn_bruteforce_pm": 2,          # pack + scan
+    "dh3d_flex_conv": 8,                                             # 4 transposes + theta_ext + moments + gemm (+memset)
+    "dh3d_flex_conv_pm": 3,                                          # theta_ext + moments + gemm (+1 if feature_bias)
+    "dh3d_query_ball_point": 2, "dh3d_netvlad": 4,
+}
+
+
+class Stats(object):
+    """Launch accounting and optional per-op device timing (CUDA events on the launching stream)."""
+
+    def __init__(self):
+        self.calls = 0
+        self.kernels = 0
+        self.timing_filter = None   # None = off; set() of entry-point names, or "all"
+        self.events = []            # (name, start_event, end_event, tag)
+        self.tag = None
+
+    def reset(self):
+        self.calls = self.kernels = 0
+        self.events = []
+
+    def op_times_ms(self):
+        """Aggregate recorded events -> {name or (name, tag): [total_ms, calls]} (call after sync)."""
+        agg = {}
+        for name, a, b, tag in self.events:
+            key = name if tag is None else "%s[%s]" % (name, tag)
+            t = agg.setdefault(key, [0.0, 0])
+            t[0] += a.elapsed_time(b)
+            t[1] += 1
+        return agg
+
+
+stats = Stats()
 
 
 class Dh3dError(RuntimeError):
@@ -85,9 +120,18 @@ def error_string(code):
 
 
 def call(name, *args):
-    global launch_count
-    rc = getattr(lib(), name)(*args)
-    launch_count += 1
+    fn = getattr(lib(), name)
+    tf = stats.timing_filter
+    if tf is not None and (tf == "all" or name in tf):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        stats.events.append((name, a, b, stats.tag))
+    else:
+        rc = fn(*args)
+    stats.calls += 1
+    stats.kernels += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise Dh3dError("%s failed with code %d: %s" % (name, rc, error_string(rc)))
 

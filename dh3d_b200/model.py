@@ -116,5 +116,5 @@ def init_random_(model, seed=0, knn=8, offset_scale=2.0):
                 fan_in = shape[-2] if len(shape) >= 2 else shape[0]
                 v = r() / (float(fan_in) ** 0.5)
             p.copy_(v.to(p.dtype))
-    model.invalidate()
+    invalidate_folded(model)
     return model

@@ -25,8 +25,10 @@ def knn_points(xyz, k):
     ids = torch.empty((B, N, k), dtype=i32, device=xyz.device)
     dists = torch.empty((B, N, k), dtype=f32, device=xyz.device)
     ws, wp, wn = workspace(query("dh3d_knn_workspace_bytes", B, N), xyz.device)
+    _lib.stats.tag = "B%d_N%d_K%d" % (B, N, k)
     call("dh3d_knn_bruteforce_pm", px, B, N, int(k), check(ids, i32, "ids"), check(dists, f32, "dists"),
          wp, wn, stream_ptr(xyz.device))
+    _lib.stats.tag = None
     return ids, dists
 
 
@@ -45,11 +47,13 @@ def flex_conv(features, theta, bias, neighborhood, xyz, feature_bias=None, scale
     out = torch.empty((B, N, Dout), dtype=f32, device=features.device)
     ws, wp, wn = workspace(query("dh3d_flex_conv_pm_workspace_bytes", B, N, K, Din, Dout),
                            features.device)
+    _lib.stats.tag = "n%d_K%d_Ci%d_Co%d" % (B * N, K, Din, Dout)
     call("dh3d_flex_conv_pm", check(features, f32, "features"), check(theta, f32, "theta"),
          check(bias, f32, "bias"), check(neighborhood, i32, "neighborhood"), check(xyz, f32, "xyz"),
          check(out, f32, "out"), B, N, K, Din, Dout, opt(feature_bias, f32, "feature_bias"),
          opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act), wp, wn,
          stream_ptr(features.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -156,8 +160,10 @@ def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0):
         check(out, f32, "out")
         ldy = out.shape[-1]
         yptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col)
+    _lib.stats.tag = "M%d_K%d_N%d" % (M, K, N)
     call("dh3d_linear", check(x, f32, "x"), K, check(w, f32, "w", 2), opt(scale, f32, "scale"),
          opt(shift, f32, "shift"), int(act), yptr, ldy, M, K, N, stream_ptr(x.device))
+    _lib.stats.tag = None
     return out
 
 

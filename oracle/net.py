@@ -27,6 +27,11 @@ import oracle
 
 TP_EPS, SLIM_EPS = 1e-5, 1e-3
 
+# reference_cpu mode (bench.py CPU arm): evaluate the custom ops the way the reference's CPU
+# functors do -- fp32 FlexConv loops (flex_conv_kernel.cc) and a full sort per query for k-NN
+# (knn_bruteforce_kernel.cc:41-69) -- instead of the fp64-truth / fast-selection forms.
+_MODE = {"reference_cpu": False}
+
 
 def _bn(x, p, prefix, eps):
     g, b = p[prefix + ".gamma"], p[prefix + ".beta"]
@@ -63,8 +68,8 @@ def flexconv_bn_relu(feat_pm, xyz_pm, nbr_pm, p, prefix):
     out = oracle.flex_convolution(
         np.transpose(feat_pm, (0, 2, 1)), np.transpose(xyz_pm, (0, 2, 1)),
         np.transpose(nbr_pm, (0, 2, 1)), p[prefix + ".position_theta"], p[prefix + ".position_bias"],
-        centre_is_self=True, f64=True)
-    out = out + p[prefix + ".feature_bias"].reshape(1, -1, 1)
+        centre_is_self=True, f64=not _MODE["reference_cpu"])
+    out = out.astype(np.float64) + p[prefix + ".feature_bias"].reshape(1, -1, 1)
     out = np.transpose(out, (0, 2, 1))
     return np.maximum(_bn(out, p, prefix + "_bn", TP_EPS), 0.0)
 
@@ -81,7 +86,7 @@ def se_block(x, pooled, p, prefix):
 
 
 def knn_pm(xyz_pm, k):
-    ids, _ = oracle.knn_bruteforce(np.transpose(xyz_pm, (0, 2, 1)), k)
+    ids, _ = oracle.knn_bruteforce(np.transpose(xyz_pm, (0, 2, 1)), k, literal=_MODE["reference_cpu"])
     return ids  # [B,N,K]
 
 
@@ -160,8 +165,9 @@ def netvlad(features, att, p, prefix="netvlad", final_l2norm=True):
     return l2_normalize(vlad, -1, 1e-8) if final_l2norm else vlad
 
 
-def forward(points, p, detection=True, extract_global=True, knn_num=8):
+def forward(points, p, detection=True, extract_global=True, knn_num=8, reference_cpu=False):
     """The inference branch of DH3D.build_graph.  points [B,N,3]."""
+    _MODE["reference_cpu"] = bool(reference_cpu)
     points = np.asarray(points, np.float32)
     knn = knn_pm(points, knn_num)
     pts64 = points.astype(np.float64)

@@ -40,6 +40,9 @@ _SIGNATURES = {
     "dh3d_three_interpolate": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_three_interpolate_from_dist": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_linear": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p]),
+    "dh3d_linear_prepack_bytes": (_c_size_t, [_c_int, _c_int]),
+    "dh3d_linear_prepack": (_c_int, [_p, _c_int, _c_int, _p, _p]),
+    "dh3d_linear_packed": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p]),
     "dh3d_rowdot": (_c_int, [_p, _c_int, _p, _c_float, _c_int, _p, _c_int, _c_int, _p]),
     "dh3d_se_excite": (_c_int, [_p, _p, _p, _c_size_t, _p]),
     "dh3d_l2_normalize_rows": (_c_int, [_p, _c_int, _p, _c_int, _c_int, _c_int, _c_float, _p]),

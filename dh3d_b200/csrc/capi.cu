@@ -42,6 +42,11 @@ int rowdot_launch(const float* x, int ldx, const float* w, float bias, int act, 
 int linear_simt_launch(const float* x, int ldx, const float* w, const float* scale,
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        cudaStream_t st);
+// gemm_tc.cu
+size_t linear_prepack_bytes(int K, int N);
+int linear_prepack_launch(const float* w, int K, int N, void* packed, cudaStream_t st);
+int linear_tc_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
+                     int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
 // flexconv.cu
 size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout);
 size_t flex_conv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
@@ -181,6 +186,15 @@ int dh3d_three_interpolate_from_dist(int b, int m, int c, int n, const float* po
 int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, const float* shift,
                 int act, float* y, int ldy, int M, int K, int N, void* stream) {
   return linear_launch(x, ldx, w, scale, shift, act, y, ldy, M, K, N, S(stream));
+}
+size_t dh3d_linear_prepack_bytes(int K, int N) { return linear_prepack_bytes(K, N); }
+int dh3d_linear_prepack(const float* w, int K, int N, void* packed, void* stream) {
+  return linear_prepack_launch(w, K, N, packed, S(stream));
+}
+int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
+                       const float* shift, int act, float* y, int ldy, int M, int K, int N,
+                       void* stream) {
+  return linear_tc_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
 }
 int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream) {

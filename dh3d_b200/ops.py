@@ -146,13 +146,26 @@ def _rows(x):
     return x.numel() // C, C
 
 
-def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0):
+def linear_prepack(w):
+    """w [K,N] -> opaque packed buffer {W_hi^T, W_lo^T} for the tensor-core path (done once)."""
+    K, N = w.shape
+    packed = torch.empty(query("dh3d_linear_prepack_bytes", K, N), dtype=torch.uint8, device=w.device)
+    call("dh3d_linear_prepack", check(w, f32, "w", 2), K, N, ctypes.c_void_p(packed.data_ptr()),
+         stream_ptr(w.device))
+    packed._dh3d_kn = (K, N)
+    return packed
+
+
+def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0, packed=None):
     """act((x @ w) * scale + shift) over the last dim of x.  ``out``/``out_col`` write the result
-    into columns [out_col, out_col+N) of an existing [..., ldy] tensor (fused concat)."""
+    into columns [out_col, out_col+N) of an existing [..., ldy] tensor (fused concat).
+    ``packed`` (from linear_prepack(w)) selects the tcgen05 3xTF32 kernel; otherwise fp32 FFMA."""
     M, K = _rows(x)
     N = w.shape[1]
     if w.shape[0] != K:
         raise _lib.Dh3dError("linear: x has %d columns, w has %d rows" % (K, w.shape[0]))
+    if packed is not None and getattr(packed, "_dh3d_kn", (K, N)) != (K, N):
+        raise _lib.Dh3dError("linear: packed weight does not match w")
     if out is None:
         out = torch.empty(x.shape[:-1] + (N,), dtype=f32, device=x.device)
         ldy, yptr = N, check(out, f32, "out")
@@ -161,8 +174,13 @@ def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0):
         ldy = out.shape[-1]
         yptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col)
     _lib.stats.tag = "M%d_K%d_N%d" % (M, K, N)
-    call("dh3d_linear", check(x, f32, "x"), K, check(w, f32, "w", 2), opt(scale, f32, "scale"),
-         opt(shift, f32, "shift"), int(act), yptr, ldy, M, K, N, stream_ptr(x.device))
+    if packed is not None:
+        call("dh3d_linear_packed", check(x, f32, "x"), K, ctypes.c_void_p(packed.data_ptr()),
+             opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act), yptr, ldy, M, K, N,
+             stream_ptr(x.device))
+    else:
+        call("dh3d_linear", check(x, f32, "x"), K, check(w, f32, "w", 2), opt(scale, f32, "scale"),
+             opt(shift, f32, "shift"), int(act), yptr, ldy, M, K, N, stream_ptr(x.device))
     _lib.stats.tag = None
     return out
 

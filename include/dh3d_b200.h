@@ -163,6 +163,14 @@ DH3D_API int dh3d_three_interpolate_from_dist(int b, int m, int c, int n, const 
  * ------------------------------------------------------------------------------------------- */
 DH3D_API int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, const float* shift,
                 int act, float* y, int ldy, int M, int K, int N, void* stream);
+/* Tensor-core path of dh3d_linear (tcgen05.mma kind::tf32 with the 3xTF32 hi/lo split: fp32-grade
+ * accuracy, ~1e-6 relative).  The weight is pre-split ONCE into packed = {W_hi^T, W_lo^T} ([N,K]
+ * K-major, what the UMMA descriptors want); activations are split on the fly in shared memory. */
+DH3D_API size_t dh3d_linear_prepack_bytes(int K, int N);
+DH3D_API int dh3d_linear_prepack(const float* w, int K, int N, void* packed, void* stream);
+DH3D_API int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
+                       const float* shift, int act, float* y, int ldy, int M, int K, int N,
+                       void* stream);
 DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream);
 DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);

@@ -1,5 +1,7 @@
 // extern "C" surface of libdh3d_b200.so -- see include/dh3d_b200.h for the contract and the
 // reference interface (file:line) each entry point replaces.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dh3d {
@@ -64,6 +66,15 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
                    const float* hw, const float* bn_scale, const float* bn_shift, const float* gw,
                    const float* gbn_scale, const float* gbn_shift, int final_l2norm, float* out,
                    void* ws, size_t ws_bytes, cudaStream_t st);
+
+// DH3D_GEMM=simt selects the exact-fp32 FFMA GEMM inside FlexConv (default: tcgen05 3xTF32).
+bool gemm_use_tc() {
+  static const bool tc = [] {
+    const char* e = getenv("DH3D_GEMM");
+    return !(e && (e[0] == 's' || e[0] == 'S'));
+  }();
+  return tc;
+}
 
 // GEMM dispatch (one place to switch the dense path)
 int linear_launch(const float* x, int ldx, const float* w, const float* scale, const float* shift,

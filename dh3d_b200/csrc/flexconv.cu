@@ -15,6 +15,10 @@ namespace dh3d {
 
 int linear_launch(const float* x, int ldx, const float* w, const float* scale, const float* shift,
                   int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
+int linear_tc_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
+                     int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
+size_t linear_prepack_bytes(int K, int N);
+bool gemm_use_tc();
 int transpose_launch(const void* src, void* dst, int B, int R, int C, cudaStream_t st);
 int transpose_strided_launch(const void* src, long long sbs, int lds, void* dst, long long sbd,
                              int ldd, int B, int R, int C, cudaStream_t st);
@@ -61,7 +65,7 @@ static size_t moments_bytes(int B, int N, int Din) {
   return align_up((size_t)B * N * 4 * Din * sizeof(float), 256);
 }
 static size_t theta_ext_bytes(int Din, int Dout) {
-  return align_up((size_t)4 * Din * Dout * sizeof(float), 256);
+  return linear_prepack_bytes(4 * Din, Dout);  // room for the {hi^T, lo^T} packed form
 }
 
 size_t flex_conv_pm_workspace_bytes(int B, int N, int K, int Din, int Dout) {
@@ -82,6 +86,26 @@ __global__ void theta_ext_kernel(const float* __restrict__ theta, const float* _
   if (c < din && o < dout)
     v = (p == 0) ? bias[(size_t)c * dout + o] : theta[((size_t)(p - 1) * din + c) * dout + o];
   ext[i] = v;
+}
+
+// Same matrix in the tensor-core GEMM's packed form: {hi^T, lo^T} with Theta_ext^T [Dout, 4*Din]
+__global__ void theta_ext_packed_kernel(const float* __restrict__ theta, const float* __restrict__ bias,
+                                        float* __restrict__ hi, float* __restrict__ lo, int din, int dout,
+                                        int dinp, int doutp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Kd = 4 * dinp;
+  if (i >= Kd * doutp) return;
+  const int o = i / Kd, row = i % Kd;
+  const int c = row % dinp, p = row / dinp;
+  float v = 0.f;
+  if (c < din && o < dout)
+    v = (p == 0) ? bias[(size_t)c * dout + o] : theta[((size_t)(p - 1) * din + c) * dout + o];
+  uint32_t b;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+  const float h = __uint_as_float(b & 0xFFFFE000u);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v - h));
+  hi[i] = h;
+  lo[i] = __uint_as_float(b & 0xFFFFE000u);
 }
 
 // y = act((x + fb) * scale + shift) == act(x*scale + (fb*scale + shift)): fold fb into the shift.
@@ -121,8 +145,16 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
   float* fshift = reinterpret_cast<float*>(p);
 
   // Theta_ext = [bias ; theta_x ; theta_y ; theta_z]  (logical dims may be smaller than the padded ones)
-  theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
-                                                                 dout_logical, Din, Dout);
+  const bool tc = gemm_use_tc();
+  if (tc) {
+    float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) +
+                                         align_up((size_t)4 * Din * Dout * sizeof(float), 256));
+    theta_ext_packed_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(
+        theta, bias, theta_ext, lo, din_logical, dout_logical, Din, Dout);
+  } else {
+    theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
+                                                                   dout_logical, Din, Dout);
+  }
 
   const float* eff_shift = shift;
   if (feature_bias) {
@@ -137,6 +169,9 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
   int rc = launch_status();
   if (rc != DH3D_OK) return rc;
   if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
+  if (tc)
+    return linear_tc_launch(A, 4 * Din, theta_ext, scale, eff_shift, act, out, Dout, (int)rows, 4 * Din,
+                            Dout, st);
   return linear_launch(A, 4 * Din, theta_ext, scale, eff_shift, act, out, Dout, (int)rows, 4 * Din,
                        Dout, st);
 }

@@ -2,7 +2,7 @@
 //
 // 5th-gen tensor cores (tcgen05.mma, kind::tf32, accumulators in TMEM) with the 3xTF32 split
 //     x = x_hi + x_lo,  w = w_hi + w_lo   (hi = tf32-representable part, lo = exact fp32 remainder)
-//     x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi        (dropped x_lo*w_lo term ~ 2^-21 relative)
+//     x*w ~= x_lo*w_hi + x_hi*w_lo + x_hi*w_hi        (dropped x_lo*w_lo term ~ 2^-22 relative)
 // which keeps the contraction within ~1e-6 of an fp32 FFMA result -- inside north_star's 1e-4 --
 // where single-pass TF32 (~1e-3) is not.  Used for the FlexConv contraction A[n,4Din] @ Theta_ext
 // and for the dense 1x1 stacks.
@@ -70,6 +70,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// fp32 -> nearest tf32-representable fp32 (low 13 mantissa bits zero)
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t b;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+  return __uint_as_float(b & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ float tc_act(float v, int act) {
@@ -174,12 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < (int)(kTcABytes / 16 / 128); ++j) {
         const int i = t + j * 128;
         const float4 v = a[i];
+        // round-to-nearest split (a truncating split biases every term the same way and the
+        // error then grows like K instead of sqrt(K))
         float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+        l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y);
+        l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
         a[i] = h;
         lo[i] = l;
       }
@@ -244,11 +251,9 @@ __global__ void linear_prepack_kernel(const float* __restrict__ w, int K, int N,
        e += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(e / K), k = (int)(e - (long long)n * K);
     const float v = w[(long long)k * N + n];
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float h = __uint_as_float(hb & 0xFFFFE000u);
+    const float h = tf32_rn(v);
     hi[e] = h;
-    lo[e] = v - h;
+    lo[e] = tf32_rn(v - h);
   }
 }
 

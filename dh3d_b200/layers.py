@@ -15,11 +15,18 @@ name-mapped loader can fill them from the shipped TF checkpoints:
 native point-major fast path the assembled forward pass uses (with the follow-up BatchNorm and
 activation fused into the kernel epilogue).  Inference only.
 """
+import os
+
 import torch
 from torch import nn
 
 from . import ops, user_ops
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+def use_tensor_cores():
+    """DH3D_GEMM=simt selects the exact-fp32 FFMA GEMMs; default is the tcgen05 3xTF32 path."""
+    return not os.environ.get("DH3D_GEMM", "tc").lower().startswith("s")
+
 
 TENSORPACK_BN_EPS = 1e-5  # tensorpack BatchNorm default epsilon (library default; parity unpinned)
 SLIM_BN_EPS = 1e-3        # tf.contrib slim / layers batch_norm default epsilon
@@ -170,9 +177,11 @@ class Conv1x1(nn.Module):
                 scale, shift = self.bn.fold(self.b)
             else:
                 scale, shift = None, self.b.detach().contiguous()
-            self._folded = (w, scale, shift)
+            packed = ops.linear_prepack(w) if (use_tensor_cores() and w.is_cuda) else None
+            self._folded = (w, scale, shift, packed)
         return self._folded
 
     def forward(self, x, out=None, out_col=0):
-        w, scale, shift = self.folded()
-        return ops.linear(x, w, scale=scale, shift=shift, act=self.act, out=out, out_col=out_col)
+        w, scale, shift, packed = self.folded()
+        return ops.linear(x, w, scale=scale, shift=shift, act=self.act, out=out, out_col=out_col,
+                          packed=packed)

@@ -31,7 +31,7 @@ def test_linear_packed_vs_fp64(M, K, N, act):
         e = ops.linear(dx, dw, scale=dsc, shift=dsh, act=0).cpu().numpy().astype(np.float64)
     e = np.maximum(e, 0) if act == 1 else (1 / (1 + np.exp(-e)) if act == 2 else e)
     err = np.abs(y.cpu().numpy() - e).max() / np.sqrt((e ** 2).mean())
-    assert err < 2e-5, err   # 3xTF32: ~1e-6; well inside the 1e-4 bar, far from 1xTF32's ~1e-3
+    assert err < 1e-5, err   # 3xTF32 with RN split: ~1e-6; the bar is 1e-4, 1xTF32 gives ~1e-3
 
 
 @pytest.mark.timeout(120)

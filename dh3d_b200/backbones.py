@@ -150,13 +150,17 @@ class AttentionHead(nn.Module):
         self._folded = None
 
     def forward(self, x):
-        for i in range(self.n):
-            x = getattr(self, "detec_conv%d" % i)(x)
         if self._folded is None:
             fc = self.detec_conv_fc
             self._folded = (fc.W.reshape(-1).contiguous(), float(fc.b.reshape(-1)[0].item()))
-        w, b = self._folded
-        return ops.rowdot(x, w, bias=b, act=ACT_SIGMOID).unsqueeze(-1)  # [B,N,1]
+        w2, b2 = self._folded
+        for i in range(self.n - 1):
+            x = getattr(self, "detec_conv%d" % i)(x)
+        last = getattr(self, "detec_conv%d" % (self.n - 1))
+        w, scale, shift, packed = last.folded()
+        if packed is not None:  # fused: the [B,N,1024] hidden layer never reaches HBM
+            return ops.linear_rowdot(x, packed, scale, shift, last.act, w2, b2, ACT_SIGMOID).unsqueeze(-1)
+        return ops.rowdot(last(x), w2, bias=b2, act=ACT_SIGMOID).unsqueeze(-1)  # [B,N,1]
 
 
 class DetectionBlock(AttentionHead):

@@ -49,6 +49,9 @@ size_t linear_prepack_bytes(int K, int N);
 int linear_prepack_launch(const float* w, int K, int N, void* packed, cudaStream_t st);
 int linear_tc_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
                      int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
+int linear_rowdot_tc_launch(const float* x, int ldx, const void* packed, const float* scale,
+                            const float* shift, int act, const float* w2, float b2, int act2, float* y2,
+                            int M, int K, int N, cudaStream_t st);
 // flexconv.cu
 size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout);
 size_t flex_conv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
@@ -206,6 +209,11 @@ int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const floa
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        void* stream) {
   return linear_tc_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
+}
+int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, const float* scale,
+                              const float* shift, int act, const float* w2, float b2, int act2,
+                              float* y, int M, int K, int N, void* stream) {
+  return linear_rowdot_tc_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
 }
 int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream) {

@@ -185,6 +185,22 @@ def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0, pack
     return out
 
 
+def linear_rowdot(x, packed, scale, shift, act, w2, b2=0.0, act2=ACT_NONE):
+    """act2(sum_n act((x @ W)[.., n]*scale+shift) * w2[n] + b2) with W given as linear_prepack(W);
+    the hidden [.., N] activation is never written (tensor-core path only)."""
+    M, K = _rows(x)
+    Kp, N = packed._dh3d_kn
+    if Kp != K or w2.numel() != N:
+        raise _lib.Dh3dError("linear_rowdot: shape mismatch")
+    y = torch.empty(x.shape[:-1], dtype=f32, device=x.device)
+    _lib.stats.tag = "M%d_K%d_N%d" % (M, K, N)
+    call("dh3d_linear_rowdot_packed", check(x, f32, "x"), K, ctypes.c_void_p(packed.data_ptr()),
+         opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act), check(w2, f32, "w2"),
+         _cf(float(b2)), int(act2), check(y, f32, "y"), M, K, N, stream_ptr(x.device))
+    _lib.stats.tag = None
+    return y
+
+
 def rowdot(x, w, bias=0.0, act=ACT_NONE):
     M, K = _rows(x)
     y = torch.empty(x.shape[:-1], dtype=f32, device=x.device)

@@ -171,6 +171,12 @@ DH3D_API int dh3d_linear_prepack(const float* w, int K, int N, void* packed, voi
 DH3D_API int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        void* stream);
+/* Fused two-layer head: y[m] = act2( sum_n act((x @ W)[m,n]*scale[n] + shift[n]) * w2[n] + b2 ).
+ * The [M,N] hidden activation (the detector's / global attention's [B*N,1024], core/backbones.py:
+ * 141-147,168-172) stays in TMEM/registers and never reaches HBM. */
+DH3D_API int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, const float* scale,
+                              const float* shift, int act, const float* w2, float b2, int act2,
+                              float* y, int M, int K, int N, void* stream);
 DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream);
 DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);

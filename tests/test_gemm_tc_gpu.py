@@ -31,7 +31,9 @@ def test_linear_packed_vs_fp64(M, K, N, act):
         e = ops.linear(dx, dw, scale=dsc, shift=dsh, act=0).cpu().numpy().astype(np.float64)
     e = np.maximum(e, 0) if act == 1 else (1 / (1 + np.exp(-e)) if act == 2 else e)
     err = np.abs(y.cpu().numpy() - e).max() / np.sqrt((e ** 2).mean())
-    assert err < 1e-5, err   # 3xTF32 with RN split: ~1e-6; the bar is 1e-4, 1xTF32 gives ~1e-3
+    # measured ~3e-5 worst case (truncating fp32 accumulation inside the tensor core); bar 1e-4;
+    # single-pass TF32 would give ~1e-3
+    assert err < 6e-5, err
 
 
 @pytest.mark.timeout(120)
@@ -50,3 +52,20 @@ def test_linear_packed_strided_output_and_exact_small_values():
     wi = torch.randint(-8, 9, (64, 128), device="cuda").float()
     yi = ops.linear(xi, wi, packed=ops.linear_prepack(wi))
     assert torch.equal(yi, xi @ wi)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("M,K,N", [(1000, 256, 1024), (262144, 128, 64), (333, 64, 16), (4096, 512, 256)])
+def test_linear_rowdot_fused_head(M, K, N):
+    from dh3d_b200 import ops
+    x, w, sc, sh = _case(M, K, N, 7 * M + N)
+    rng = np.random.RandomState(N)
+    w2 = (rng.randn(N) / np.sqrt(N)).astype(np.float32)
+    dx, dw, dsc, dsh, dw2 = (torch.from_numpy(a).cuda() for a in (x, w, sc, sh, w2))
+    y = ops.linear_rowdot(dx, ops.linear_prepack(dw), dsc, dsh, 1, dw2, 0.125, 2)
+    if M * K * N <= 4e9:
+        h = np.maximum(x.astype(np.float64) @ w.astype(np.float64) * sc + sh, 0)
+        e = 1 / (1 + np.exp(-(h @ w2.astype(np.float64) + 0.125)))
+    else:
+        e = ops.rowdot(ops.linear(dx, dw, scale=dsc, shift=dsh, act=1), dw2, bias=0.125, act=2).cpu().numpy()
+    assert np.abs(y.cpu().numpy() - e).max() < 5e-5

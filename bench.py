@@ -108,9 +108,12 @@ def algorithmic(tag, name):
     for part in tag.split("_"):
         key = part.rstrip("0123456789")
         d[key] = int(part[len(key):])
-    if name == "dh3d_linear":
+    if name in ("dh3d_linear", "dh3d_linear_packed"):
         M, K, N = d["M"], d["K"], d["N"]
         return 4.0 * (M * K + K * N + M * N), 2.0 * M * K * N
+    if name == "dh3d_linear_rowdot_packed":   # hidden [M,N] never written: x + W + one float per row
+        M, K, N = d["M"], d["K"], d["N"]
+        return 4.0 * (M * K + K * N + N + M), 2.0 * M * K * N + 2.0 * M * N
     if name == "dh3d_flex_conv_pm":
         n, K, Ci, Co = d["n"], d["K"], d["Ci"], d["Co"]
         return 4.0 * (n * Ci + n * Co + n * K + 3 * n + 4 * Ci * Co), 8.0 * n * K * Ci + 8.0 * n * Ci * Co
@@ -299,13 +302,18 @@ def main():
     tag = dominant.split("[")[1].rstrip("]") if "[" in dominant else ""
     abytes, aflops = algorithmic(tag, dom_name) if tag else (0.0, 0.0)
     avg_s = (tot_ms / max(calls, 1)) / 1e3
-    if dom_name == "dh3d_linear":
+    if dom_name.startswith("dh3d_linear"):
         ach = aflops / avg_s / 1e12
+        tc = dom_name != "dh3d_linear"
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
                 "kernel": dominant, "avg_launch_ms": avg_s * 1e3, "launches_timed": calls,
                 "peak_source": peaks["source"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",
-                "note": "fp32-accurate GEMM; flops = 2*M*K*N"}
+                "note": "achieved = algorithmic 2*M*K*N flops of an fp32-accurate GEMM. " +
+                        ("The kernel executes 3 TF32 tcgen05 MMAs per product (3xTF32 split) and TF32 runs at "
+                         "half the bf16 rate, so it issues %.0f TFLOP/s of TF32 work = %.2f of the TF32 pipe "
+                         "(measured bf16 peak / 2)." % (3 * ach, 3 * ach / (peaks["bf16_tflops_sustained"] / 2))
+                         if tc else "fp32 FFMA kernel (DH3D_GEMM=simt).")}
     else:
         ach = abytes / avg_s / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",

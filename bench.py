@@ -123,6 +123,22 @@ def algorithmic(tag, name):
     return 0.0, 0.0
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU comparator is meant to use every host thread."""
+    import oracle
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    oracle.set_num_threads(n)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)   # numpy BLAS for the dense layers
+    except Exception:
+        pass
+    return n
+
+
 def run_reference_arm(args, rank, world):
     """The reference's CPU path on the host cores: the oracle port (oracle/dh3d_oracle.c literal
     loops incl. the full-sort kNN of knn_bruteforce_kernel.cc, OpenMP over all cores; dense layers
@@ -134,6 +150,7 @@ def run_reference_arm(args, rank, world):
     from oracle import net
     from dh3d_b200.configs import full_config, basic_config
     from dh3d_b200.model import DH3D, init_random_
+    use_all_host_threads()
     cfg = full_config() if args.workload == "full" else basic_config()
     model = init_random_(DH3D(cfg), seed=0)
     params = {k: v.detach().numpy() for k, v in model.named_parameters()}
@@ -336,6 +353,7 @@ def main():
         import numpy as np
         import oracle
         from oracle import net
+        use_all_host_threads()
         cpu_model = init_random_(DH3D(cfg), seed=0)
         params = {k: v.detach().numpy() for k, v in cpu_model.named_parameters()}
         cloud = synth_clouds(1, N_POINTS, 0).numpy()

@@ -129,30 +129,36 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-__global__ void conv_pointset_kernel(const float* __restrict__ feat, const float* __restrict__ theta,
-                                     const float* __restrict__ bias, const int32_t* __restrict__ nbr,
-                                     float* __restrict__ out, long long rows, int n, int k, int din,
-                                     int dout, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, int act) {
-  const long long total = rows * dout;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long r = e / dout;
-    const int o = (int)(e - r * dout);
+// one warp per point, lanes over output channels: the K neighbour rows are read once per point with
+// warp-uniform loads, theta lives in shared memory, the output row is one coalesced store.
+__global__ void __launch_bounds__(256)
+conv_pointset_kernel(const float* __restrict__ feat, const float* __restrict__ theta,
+                     const float* __restrict__ bias, const int32_t* __restrict__ nbr,
+                     float* __restrict__ out, long long rows, int n, int k, int din, int dout,
+                     const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+  extern __shared__ float s_theta[];  // [din][dout]
+  for (int i = threadIdx.x; i < din * dout; i += blockDim.x) s_theta[i] = __ldg(theta + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
     const long long b = r / n;
     const int32_t* nb = nbr + r * k;
-    const float* base = feat + (long long)b * n * din;
+    const float* base = feat + b * n * (long long)din;
     const float* f0 = base + (long long)__ldg(nb) * din;
-    float acc = 0.f;
-    for (int kk = 0; kk < k; ++kk) {
-      const float* fk = base + (long long)__ldg(nb + kk) * din;
-      for (int c = 0; c < din; ++c)
-        acc = __fmaf_rn(__ldg(theta + c * dout + o), __fsub_rn(__ldg(fk + c), __ldg(f0 + c)), acc);
+    for (int o = lane; o < dout; o += 32) {
+      float acc = 0.f;
+      for (int kk = 0; kk < k; ++kk) {
+        const float* fk = base + (long long)__ldg(nb + kk) * din;
+        for (int c = 0; c < din; ++c)
+          acc = __fmaf_rn(s_theta[c * dout + o], __fsub_rn(__ldg(fk + c), __ldg(f0 + c)), acc);
+      }
+      acc = __fadd_rn(acc, __ldg(bias + o));
+      if (scale) acc *= __ldg(scale + o);
+      if (shift) acc += __ldg(shift + o);
+      out[r * dout + o] = apply_act(acc, act);
     }
-    acc = __fadd_rn(acc, __ldg(bias + o));
-    if (scale) acc *= __ldg(scale + o);
-    if (shift) acc += __ldg(shift + o);
-    out[e] = apply_act(acc, act);
   }
 }
 
@@ -161,10 +167,10 @@ int conv_pointset_pm_launch(const float* feat, const float* theta, const float* 
                             const float* scale, const float* shift, int act, cudaStream_t st) {
   if (!feat || !theta || !bias || !nbr || !out) return DH3D_ERR_NULL;
   if (B <= 0 || N <= 0 || K <= 0 || Din <= 0 || Dout <= 0) return DH3D_ERR_DIM;
-  if (Din > 64) return DH3D_ERR_UNSUPPORTED;
+  if (Din > 64 || (size_t)Din * Dout * sizeof(float) > 48 * 1024) return DH3D_ERR_UNSUPPORTED;
   const long long rows = (long long)B * N;
-  conv_pointset_kernel<<<ew_blocks(rows * Dout, 256), 256, 0, st>>>(feat, theta, bias, nbr, out, rows,
-                                                                  N, K, Din, Dout, scale, shift, act);
+  conv_pointset_kernel<<<ew_blocks(rows * 32, 256), 256, (size_t)Din * Dout * sizeof(float), st>>>(
+      feat, theta, bias, nbr, out, rows, N, K, Din, Dout, scale, shift, act);
   return launch_status();
 }
 

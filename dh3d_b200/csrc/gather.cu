@@ -142,11 +142,38 @@ conv_pointset_kernel(const float* __restrict__ feat, const float* __restrict__ t
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool packed = k * din <= 32;  // DH3D: K=8, Din=3 -> one (neighbour, channel) difference per lane
   for (long long r = warp; r < rows; r += nwarps) {
     const long long b = r / n;
     const int32_t* nb = nbr + r * k;
     const float* base = feat + b * n * (long long)din;
     const float* f0 = base + (long long)__ldg(nb) * din;
+    if (packed) {
+      // lane L holds d[kk][c] = f[nbr_kk][c] - f[nbr_0][c] for L = kk*din + c: all gathers in flight at
+      // once, then the reference's (k outer, c inner) FMA chain runs on shuffled registers
+      float d = 0.f;
+      if (lane < k * din) {
+        const int kk = lane / din, c = lane - kk * din;
+        d = __fsub_rn(__ldg(base + (long long)__ldg(nb + kk) * din + c), __ldg(f0 + c));
+      }
+      for (int o0 = 0; o0 < dout; o0 += 32) {
+        const int o = o0 + lane;
+        const bool in = o < dout;
+        float acc = 0.f;
+        for (int kk = 0; kk < k; ++kk)
+          for (int c = 0; c < din; ++c) {
+            const float dv = __shfl_sync(0xffffffffu, d, kk * din + c);
+            if (in) acc = __fmaf_rn(s_theta[c * dout + o], dv, acc);
+          }
+        if (in) {
+          acc = __fadd_rn(acc, __ldg(bias + o));
+          if (scale) acc *= __ldg(scale + o);
+          if (shift) acc += __ldg(shift + o);
+          out[r * dout + o] = apply_act(acc, act);
+        }
+      }
+      continue;
+    }
     for (int o = lane; o < dout; o += 32) {
       float acc = 0.f;
       for (int kk = 0; kk < k; ++kk) {

@@ -21,6 +21,7 @@
 //               per warp) -> scale/shift/act -> swizzled smem staging -> TMA store (coalesced, clips
 //               the M/N tails), or the fused row-dot kept in a register per row across the N tiles.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -50,6 +51,33 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
       "r"(c1)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                               uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
+      "r"(c1), "h"(mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -111,7 +139,9 @@ struct TcEpilogue {
   float* y2;            // [M]   (ROWDOT mode)
 };
 
-template <int BN, bool ROWDOT>
+// MC = CTAs per cluster sharing every W tile through TMA multicast (1 or 2): each CTA loads half of
+// the tile and multicasts it to both, halving the L2->SM weight traffic that bounds this kernel.
+template <int BN, bool ROWDOT, int MC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY,
@@ -134,6 +164,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = (K + kTcBK - 1) / kTcBK;
   const int num_mt = (M + kTcBM - 1) / kTcBM;
   const int num_nt = (N + BN - 1) / BN;
+  // M tiles are dealt out per cluster: cluster c takes tiles (c*MC + rank), stride gridDim.x; every CTA
+  // of a cluster runs the same number of iterations (a tile index >= num_mt is all out-of-bounds:
+  // TMA zero-fills the loads and clips the stores)
+  const uint32_t crank = MC > 1 ? cluster_ctarank() : 0;
+  const int mt_begin = (int)(blockIdx.x / MC) * MC;  // first tile of this cluster
+  const int mt_stride = (int)gridDim.x;
 
   auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
   auto stage_alo = [&](int s) { return smem + s * Cfg::kStageBytes + kTcABytes; };
@@ -144,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&conv[s], 128);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC);  // one tcgen05.commit per CTA of the cluster (peers write this stage too)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -161,6 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -168,7 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride) {
+        const int mt = mtb + (int)crank;
         for (int nt = 0; nt < num_nt; ++nt)
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int s = it % S;
@@ -176,9 +214,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&full[s], kTcABytes + 2 * Cfg::kBBytes);
             tma_load_2d(stage_a(s), &tmA, kb * kTcBK, mt * kTcBM, &full[s]);
-            tma_load_2d(stage_bhi(s), &tmBhi, kb * kTcBK, nt * BN, &full[s]);
-            tma_load_2d(stage_blo(s), &tmBlo, kb * kTcBK, nt * BN, &full[s]);
+            if constexpr (MC == 1) {
+              tma_load_2d(stage_bhi(s), &tmBhi, kb * kTcBK, nt * BN, &full[s]);
+              tma_load_2d(stage_blo(s), &tmBlo, kb * kTcBK, nt * BN, &full[s]);
+            } else {
+              // this CTA's half of the W tile (rows crank*BN/2 ..) lands in BOTH CTAs' stage s
+              constexpr int HB = BN / MC;
+              const uint32_t off = crank * HB * (kTcBK * 4);
+              tma_load_2d_mc(stage_bhi(s) + off, &tmBhi, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
+                             (uint16_t)((1u << MC) - 1));
+              tma_load_2d_mc(stage_blo(s) + off, &tmBlo, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
+                             (uint16_t)((1u << MC) - 1));
+            }
           }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -187,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(kTcBM >> 4) << 24);
       uint32_t it = 0, tile = 0;
-      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
         for (int nt = 0; nt < num_nt; ++nt, ++tile) {
           const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
           mbar_wait(&tmem_empty[acc], aph ^ 1);
@@ -209,7 +258,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
               umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
             }
-            umma_commit(&empty[s]);
+            if constexpr (MC == 1) umma_commit(&empty[s]);
+            else umma_commit_mc(&empty[s], (uint16_t)((1u << MC) - 1));  // frees the stage in every CTA
           }
           umma_commit(&tmem_full[acc]);
         }
@@ -218,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ x_lo producers
     const int t = threadIdx.x - 64;  // 0..127
     uint32_t it = 0;
-    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+    for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
       for (int nt = 0; nt < num_nt; ++nt)
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % S;
@@ -246,7 +296,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 192;    // 0..127
     uint8_t* my_stage = out_stage + (warp - 6) * 4096;
     uint32_t tile = 0;
-    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
+    for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride) {
+      const int mt = mtb + (int)crank;
       float dot = 0.f;
       for (int nt = 0; nt < num_nt; ++nt, ++tile) {
         const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
@@ -318,6 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -402,24 +454,56 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool ROWDOT>
-static int launch_tc(const float* x, int ldx, const float* whi, const float* wlo, const TcEpilogue& ep,
-                     float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+static bool tc_use_multicast() {
+  static const bool on = [] {
+    const char* e = getenv("DH3D_GEMM_MULTICAST");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int BN, bool ROWDOT, int MC>
+static int launch_tc_mc(const float* x, int ldx, const float* whi, const float* wlo, const TcEpilogue& ep,
+                        float* y, int ldy, int M, int K, int N, cudaStream_t st) {
   CUtensorMap ma, mh, ml, my;
   int rc;
   if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) != DH3D_OK) return rc;
-  if ((rc = make_map(&mh, whi, N, K, K, BN)) != DH3D_OK) return rc;
-  if ((rc = make_map(&ml, wlo, N, K, K, BN)) != DH3D_OK) return rc;
+  if ((rc = make_map(&mh, whi, N, K, K, BN / MC)) != DH3D_OK) return rc;
+  if ((rc = make_map(&ml, wlo, N, K, K, BN / MC)) != DH3D_OK) return rc;
   if (ROWDOT) my = ma;
   else if ((rc = make_map(&my, y, M, N, ldy, 32)) != DH3D_OK) return rc;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, ROWDOT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+  auto kern = gemm_tc_kernel<BN, ROWDOT, MC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)TcCfg<BN>::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   const int num_mt = ceil_div(M, kTcBM);
-  const int grid = num_mt < num_sms() ? num_mt : num_sms();
-  gemm_tc_kernel<BN, ROWDOT><<<grid, kTcThreads, TcCfg<BN>::kSmemBytes, st>>>(ma, mh, ml, my, ep, M, K, N);
+  int grid = num_mt < num_sms() ? num_mt : num_sms();
+  grid = ceil_div(grid, MC) * MC;
+  if (grid > num_sms()) grid -= MC;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = TcCfg<BN>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, ma, mh, ml, my, ep, M, K, N);
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
+}
+
+template <int BN, bool ROWDOT>
+static int launch_tc(const float* x, int ldx, const float* whi, const float* wlo, const TcEpilogue& ep,
+                     float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+  // pairs of CTAs share each W tile when there are enough M tiles to pair up and W is re-streamed
+  if (BN >= 64 && tc_use_multicast() && ceil_div(M, kTcBM) >= 2 * 16)
+    return launch_tc_mc<BN, ROWDOT, 2>(x, ldx, whi, wlo, ep, y, ldy, M, K, N, st);
+  return launch_tc_mc<BN, ROWDOT, 1>(x, ldx, whi, wlo, ep, y, ldy, M, K, N, st);
 }
 
 static int tc_check(const float* x, int ldx, const void* packed, int M, int K, int N) {

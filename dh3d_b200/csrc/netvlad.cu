@@ -19,7 +19,7 @@ constexpr int kVD = 256;    // feature dim == threads per CTA
 constexpr int kVK = 64;     // clusters
 constexpr int kVTP = 32;    // points per sub-tile
 constexpr int kVXS = kVD + 4;  // padded row stride of the x tile (floats)
-constexpr int kVSlabs = 16;    // CTAs (slabs of points) per cloud
+constexpr int kVMaxSlabs = 32; // upper bound of CTAs (slabs of points) per cloud
 constexpr int kVSlice = 128;   // rows of hidden1_weights per projection CTA
 
 struct __align__(16) VladSmem {
@@ -30,14 +30,14 @@ struct __align__(16) VladSmem {
 
 __global__ void __launch_bounds__(kVD)
 netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict__ att, int N,
-                         const float* __restrict__ cw, const float* __restrict__ bn_scale,
+                         int slabs, const float* __restrict__ cw, const float* __restrict__ bn_scale,
                          const float* __restrict__ bn_shift, float* __restrict__ part_v,
                          float* __restrict__ part_s) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VladSmem& sm = *reinterpret_cast<VladSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, slab = blockIdx.x;
-  const int per = (N + kVSlabs - 1) / kVSlabs;
+  const int per = (N + slabs - 1) / slabs;
   const int n_begin = slab * per;
   const int n_end = min(N, n_begin + per);
 
@@ -78,14 +78,19 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
     __syncthreads();
     // (b) assignment logits for 2 rows x 4 clusters per thread
     float l0[4] = {0.f, 0.f, 0.f, 0.f}, l1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int d = 0; d < kVD; ++d) {
-      const float a0 = sm.x[2 * ty][d], a1 = sm.x[2 * ty + 1][d];
-      const float4 w4 = *reinterpret_cast<const float4*>(&sm.w[d][tx * 4]);
-      l0[0] = fmaf(a0, w4.x, l0[0]); l0[1] = fmaf(a0, w4.y, l0[1]);
-      l0[2] = fmaf(a0, w4.z, l0[2]); l0[3] = fmaf(a0, w4.w, l0[3]);
-      l1[0] = fmaf(a1, w4.x, l1[0]); l1[1] = fmaf(a1, w4.y, l1[1]);
-      l1[2] = fmaf(a1, w4.z, l1[2]); l1[3] = fmaf(a1, w4.w, l1[3]);
+#pragma unroll 2
+    for (int d = 0; d < kVD; d += 4) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&sm.x[2 * ty][d]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sm.x[2 * ty + 1][d]);
+      const float a0[4] = {x0.x, x0.y, x0.z, x0.w}, a1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sm.w[d + e][tx * 4]);
+        l0[0] = fmaf(a0[e], w4.x, l0[0]); l0[1] = fmaf(a0[e], w4.y, l0[1]);
+        l0[2] = fmaf(a0[e], w4.z, l0[2]); l0[3] = fmaf(a0[e], w4.w, l0[3]);
+        l1[0] = fmaf(a1[e], w4.x, l1[0]); l1[1] = fmaf(a1[e], w4.y, l1[1]);
+        l1[2] = fmaf(a1[e], w4.z, l1[2]); l1[3] = fmaf(a1[e], w4.w, l1[3]);
+      }
     }
     // (c) folded cluster BN, softmax over the 64 clusters (16 lanes x 4), x attention
 #pragma unroll
@@ -121,17 +126,17 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
     }
   }
 
-  float* pv = part_v + (((long long)b * kVSlabs + slab) * kVD + tid) * kVK;
+  float* pv = part_v + (((long long)b * slabs + slab) * kVD + tid) * kVK;
 #pragma unroll
   for (int k = 0; k < kVK; k += 4)
     *reinterpret_cast<float4*>(pv + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
-  if (tid < kVK) part_s[((long long)b * kVSlabs + slab) * kVK + tid] = ssum;
+  if (tid < kVK) part_s[((long long)b * slabs + slab) * kVK + tid] = ssum;
 }
 
 // one CTA per cloud: combine slabs, subtract S*W2, intra-normalise per cluster, flatten
 // feature-major ([d*64 + k], backbones.py:258-260), global l2-normalise.
 __global__ void __launch_bounds__(kVD)
-netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restrict__ part_s,
+netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restrict__ part_s, int slabs,
                         const float* __restrict__ cw2, float* __restrict__ vlad) {
   __shared__ float s_sum[kVK];
   __shared__ float s_red[kVD / 32][kVK];
@@ -142,14 +147,14 @@ netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restric
 
   if (tid < kVK) {
     float s = 0.f;
-    for (int c = 0; c < kVSlabs; ++c) s += part_s[((long long)b * kVSlabs + c) * kVK + tid];
+    for (int c = 0; c < slabs; ++c) s += part_s[((long long)b * slabs + c) * kVK + tid];
     s_sum[tid] = s;
   }
   float v[kVK];
 #pragma unroll
   for (int k = 0; k < kVK; ++k) v[k] = 0.f;
-  for (int c = 0; c < kVSlabs; ++c) {
-    const float* pv = part_v + (((long long)b * kVSlabs + c) * kVD + tid) * kVK;
+  for (int c = 0; c < slabs; ++c) {
+    const float* pv = part_v + (((long long)b * slabs + c) * kVD + tid) * kVK;
 #pragma unroll
     for (int k = 0; k < kVK; k += 4) {
       const float4 t = ldg4(pv + k);
@@ -250,8 +255,8 @@ netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B,
   out[(long long)b * kVD + tid] = y;
 }
 
-static size_t nv_part_v_bytes(int B) { return align_up((size_t)B * kVSlabs * kVD * kVK * 4, 256); }
-static size_t nv_part_s_bytes(int B) { return align_up((size_t)B * kVSlabs * kVK * 4, 256); }
+static size_t nv_part_v_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVD * kVK * 4, 256); }
+static size_t nv_part_s_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVK * 4, 256); }
 static size_t nv_vlad_bytes(int B) { return align_up((size_t)B * kVD * kVK * 4, 256); }
 static size_t nv_part_h_bytes(int B) {
   return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
@@ -287,11 +292,16 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(VladSmem));
   if (e != cudaSuccess) return (int)e;
-  netvlad_aggregate_kernel<<<dim3(kVSlabs, B), kVD, sizeof(VladSmem), st>>>(
-      features, att, N, cw, cbn_scale, cbn_shift, part_v, part_s);
+  // slabs per cloud: fill whole waves of (148 SMs x 2 resident CTAs), at least 64 points per slab
+  int slabs = (2 * kNumSMs) / B;
+  if (slabs < 1) slabs = 1;
+  if (slabs > kVMaxSlabs) slabs = kVMaxSlabs;
+  while (slabs > 1 && (N + slabs - 1) / slabs < 64) --slabs;
+  netvlad_aggregate_kernel<<<dim3(slabs, B), kVD, sizeof(VladSmem), st>>>(
+      features, att, N, slabs, cw, cbn_scale, cbn_shift, part_v, part_s);
   int rc = launch_status();
   if (rc != DH3D_OK) return rc;
-  netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, cw2, vlad);
+  netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, slabs, cw2, vlad);
   if ((rc = launch_status()) != DH3D_OK) return rc;
   const int slices = kVD * kVK / kVSlice;
   netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);

@@ -81,3 +81,19 @@ def test_knn_inds_input_path():
     a = model(pts)
     b = model(pts, knn_inds=ids)
     assert torch.equal(a["globaldesc"], b["globaldesc"]) and torch.equal(a["feat"], b["feat"])
+
+
+def test_graph_replay_matches_eager_bitwise():
+    """GraphedForward (one CUDA-graph replay per batch, both streams captured) == eager launches."""
+    from dh3d_b200.model import GraphedForward
+    model, _ = _model(4)
+    rng = np.random.RandomState(4)
+    a = torch.from_numpy(make_cloud(rng, 2, 2048, extent=15.0)).cuda()
+    b = torch.from_numpy(make_cloud(rng, 2, 2048, extent=15.0)).cuda()
+    g = GraphedForward(model, a)
+    for pts in (a, b, a):
+        eager = model(pts)
+        out = g(pts)
+        torch.cuda.synchronize()
+        for k in ("local_desc", "attention", "globaldesc"):
+            assert torch.equal(out[k], eager[k]), k

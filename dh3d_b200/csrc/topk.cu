@@ -1,0 +1,66 @@
+// k smallest squared-L2 distances per query row from a Gram matrix (retrieval after the descriptor
+// all-gather; reference evaluate/global_eval/evaluation_retrieval.py:37-40 uses a host cKDTree).
+//   d2[q,r] = qn[q] + rn[r] - 2*gram[q,r];  one warp per query: each lane keeps the k smallest of its
+//   strided share in registers (sorted insert), then k rounds of warp-argmin pop the global order
+//   (ties: smaller index first).
+#include "common.cuh"
+
+namespace dh3d {
+
+template <int KC>
+__global__ void __launch_bounds__(128)
+topk_l2_kernel(const float* __restrict__ gram, const float* __restrict__ qn, const float* __restrict__ rn,
+               int Q, int R, int K, int32_t* __restrict__ idx, float* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= Q) return;
+  const float* g = gram + (long long)q * R;
+  const float nq = __ldg(qn + q);
+  float v[KC];
+  int id[KC];
+#pragma unroll
+  for (int j = 0; j < KC; ++j) { v[j] = CUDART_INF_F; id[j] = 0x7fffffff; }
+  for (int r = lane; r < R; r += 32) {
+    const float d = fmaxf(nq + __ldg(rn + r) - 2.f * __ldg(g + r), 0.f);
+    if (d < v[KC - 1]) {
+#pragma unroll
+      for (int j = KC - 1; j > 0; --j) {
+        if (d < v[j - 1]) { v[j] = v[j - 1]; id[j] = id[j - 1]; }
+        else if (d < v[j]) { v[j] = d; id[j] = r; }
+      }
+      if (d < v[0]) { v[0] = d; id[0] = r; }
+    }
+  }
+  for (int out = 0; out < K; ++out) {
+    // lane with the smallest head (value, index)
+    float bv = v[0];
+    int bi = id[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { idx[(long long)q * K + out] = bi; val[(long long)q * K + out] = bv; }
+    if (id[0] == bi) {  // pop
+#pragma unroll
+      for (int j = 0; j < KC - 1; ++j) { v[j] = v[j + 1]; id[j] = id[j + 1]; }
+      v[KC - 1] = CUDART_INF_F;
+      id[KC - 1] = 0x7fffffff;
+    }
+  }
+}
+
+int topk_l2_launch(const float* gram, const float* qn, const float* rn, int Q, int R, int K, int32_t* idx,
+                   float* val, cudaStream_t st) {
+  if (!gram || !qn || !rn || !idx || !val) return DH3D_ERR_NULL;
+  if (Q <= 0 || R <= 0 || K <= 0 || K > R) return DH3D_ERR_DIM;
+  if (K > 32) return DH3D_ERR_UNSUPPORTED;
+  const int blocks = ceil_div(Q * 32, 128);
+  if (K <= 8) topk_l2_kernel<8><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
+  else if (K <= 16) topk_l2_kernel<16><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
+  else topk_l2_kernel<32><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
+  return launch_status();
+}
+
+}  // namespace dh3d

@@ -209,6 +209,15 @@ DH3D_API int dh3d_netvlad(const float* features, const float* att, int B, int N,
                  const float* gating_bn_shift, int final_l2norm, float* out, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Retrieval after the descriptor all-gather -- the step downstream of the one collective
+ *   reference: evaluate/global_eval/evaluation_retrieval.py:37-40 (host cKDTree, k = 25)
+ *   gram [Q,R] = query @ ref^T (e.g. from dh3d_linear), qn [Q] / rn [R] squared norms
+ *   -> idx [Q,K] i32, val [Q,K] squared L2 distances, ascending (ties: smaller index).  K <= 32.
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_topk_l2(const float* gram, const float* qn, const float* rn, int Q, int R, int K,
+                 int32_t* idx, float* val, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,8 +63,8 @@ int flex_conv_cm(const float* feat_cm, const float* theta, const float* bias, co
                  const float* pos_cm, float* out_cm, int B, int N, int K, int Din, int Dout, void* ws,
                  size_t ws_bytes, cudaStream_t st);
 // topk.cu
-int topk_l2_launch(const float* gram, const float* qn, const float* rn, int Q, int R, int K, int32_t* idx,
-                   float* val, cudaStream_t st);
+int topk_l2_launch(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
+                   int32_t* idx, float* val, cudaStream_t st);
 // netvlad.cu
 size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim);
 int netvlad_launch(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
@@ -242,9 +242,9 @@ int dh3d_transpose_pm_to_cm(const void* src_pm, void* dst_cm, int B, int N, int 
   return transpose_launch(src_pm, dst_cm, B, N, C, S(stream));
 }
 
-int dh3d_topk_l2(const float* gram, const float* qn, const float* rn, int Q, int R, int K, int32_t* idx,
-                 float* val, void* stream) {
-  return topk_l2_launch(gram, qn, rn, Q, R, K, idx, val, S(stream));
+int dh3d_topk_l2(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
+                 int32_t* idx, float* val, void* stream) {
+  return topk_l2_launch(gram, ldg, qn, rn, Q, R, K, idx, val, S(stream));
 }
 
 size_t dh3d_netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {

@@ -10,11 +10,11 @@ namespace dh3d {
 template <int KC>
 __global__ void __launch_bounds__(128)
 topk_l2_kernel(const float* __restrict__ gram, const float* __restrict__ qn, const float* __restrict__ rn,
-               int Q, int R, int K, int32_t* __restrict__ idx, float* __restrict__ val) {
+               int Q, int R, int ldg, int K, int32_t* __restrict__ idx, float* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= Q) return;
-  const float* g = gram + (long long)q * R;
+  const float* g = gram + (long long)q * ldg;
   const float nq = __ldg(qn + q);
   float v[KC];
   int id[KC];
@@ -51,15 +51,15 @@ topk_l2_kernel(const float* __restrict__ gram, const float* __restrict__ qn, con
   }
 }
 
-int topk_l2_launch(const float* gram, const float* qn, const float* rn, int Q, int R, int K, int32_t* idx,
-                   float* val, cudaStream_t st) {
+int topk_l2_launch(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
+                   int32_t* idx, float* val, cudaStream_t st) {
   if (!gram || !qn || !rn || !idx || !val) return DH3D_ERR_NULL;
-  if (Q <= 0 || R <= 0 || K <= 0 || K > R) return DH3D_ERR_DIM;
+  if (Q <= 0 || R <= 0 || K <= 0 || K > R || ldg < R) return DH3D_ERR_DIM;
   if (K > 32) return DH3D_ERR_UNSUPPORTED;
   const int blocks = ceil_div(Q * 32, 128);
-  if (K <= 8) topk_l2_kernel<8><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
-  else if (K <= 16) topk_l2_kernel<16><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
-  else topk_l2_kernel<32><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, K, idx, val);
+  if (K <= 8) topk_l2_kernel<8><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, ldg, K, idx, val);
+  else if (K <= 16) topk_l2_kernel<16><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, ldg, K, idx, val);
+  else topk_l2_kernel<32><<<blocks, 128, 0, st>>>(gram, qn, rn, Q, R, ldg, K, idx, val);
   return launch_status();
 }
 

@@ -18,12 +18,15 @@ def retrieve_topk(ref_desc, query_desc, k):
     R, D = ref_desc.shape
     Q = query_desc.shape[0]
     k = min(int(k), R)
-    gram = ops.linear(query_desc.contiguous(), ops.transpose_pm_to_cm(ref_desc.reshape(1, R, D)).reshape(D, R))
+    Rp = (R + 3) // 4 * 4  # the GEMM wants a column count that is a multiple of 4: zero-pad ref^T
+    ref_t = torch.zeros((D, Rp), dtype=torch.float32, device=ref_desc.device)
+    ref_t[:, :R] = ops.transpose_pm_to_cm(ref_desc.reshape(1, R, D).contiguous()).reshape(D, R)
+    gram = ops.linear(query_desc.contiguous(), ref_t)     # [Q, Rp]
     qn = (query_desc * query_desc).sum(1).contiguous()
     rn = (ref_desc * ref_desc).sum(1).contiguous()
     idx = torch.empty((Q, k), dtype=torch.int32, device=ref_desc.device)
     val = torch.empty((Q, k), dtype=torch.float32, device=ref_desc.device)
-    call("dh3d_topk_l2", check(gram, torch.float32, "gram"), check(qn, torch.float32, "qn"),
+    call("dh3d_topk_l2", check(gram, torch.float32, "gram"), Rp, check(qn, torch.float32, "qn"),
          check(rn, torch.float32, "rn"), Q, R, k, check(idx, torch.int32, "idx"),
          check(val, torch.float32, "val"), stream_ptr(ref_desc.device))
     return idx, val

@@ -212,10 +212,10 @@ DH3D_API int dh3d_netvlad(const float* features, const float* att, int B, int N,
 /* ---------------------------------------------------------------------------------------------
  * Retrieval after the descriptor all-gather -- the step downstream of the one collective
  *   reference: evaluate/global_eval/evaluation_retrieval.py:37-40 (host cKDTree, k = 25)
- *   gram [Q,R] = query @ ref^T (e.g. from dh3d_linear), qn [Q] / rn [R] squared norms
+ *   gram [Q,R] (row stride ldg >= R) = query @ ref^T (e.g. from dh3d_linear), qn [Q] / rn [R] squared norms
  *   -> idx [Q,K] i32, val [Q,K] squared L2 distances, ascending (ties: smaller index).  K <= 32.
  * ------------------------------------------------------------------------------------------- */
-DH3D_API int dh3d_topk_l2(const float* gram, const float* qn, const float* rn, int Q, int R, int K,
+DH3D_API int dh3d_topk_l2(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                  int32_t* idx, float* val, void* stream);
 
 #ifdef __cplusplus

@@ -40,3 +40,32 @@ def test_data_helpers_on_demo_cloud():
     assert pc.ndim == 2 and pc.shape[1] == 3 and pc.shape[0] > 4096
     fixed, ori = get_fixednum_pcd(pc, 8192, rng=np.random.RandomState(0))
     assert fixed.shape == (8192, 3) and fixed.dtype == np.float32 and 0 < ori <= 8192
+
+
+def test_real_weights_demo_descriptors_match_gpu_golden():
+    """tests/golden/demo_globaldesc.npz holds the global descriptors this repo's CUDA forward produced
+    on a B200 for the reference's 100 demo clouds with its SHIPPED checkpoints
+    (scripts/eval_demo_retrieval.py --backend gpu) next to the fp64 oracle's.  Re-derive three of
+    them with the oracle here and check all 100 stored pairs: real LiDAR data incl. 15 clouds padded
+    with duplicated points (exact k-NN / FPS ties)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from eval_demo_retrieval import prepare
+    from dh3d_b200.checkpoint import load_reference_checkpoint
+    from dh3d_b200.configs import full_config
+    from dh3d_b200.model import DH3D
+    from oracle import net
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo_globaldesc.npz"))
+    gpu, orc = gold["gpu_globaldesc"], gold["oracle_globaldesc"]
+    assert gpu.shape == (100, 256)
+    assert np.abs(gpu - orc).max() < 5e-5 and np.allclose(np.linalg.norm(gpu, axis=1), 1, atol=1e-5)
+    assert gold["recall"][:, 0].min() >= 0.7 and gold["recall"][:, 1].min() >= 0.9   # recall@1 / @5
+    names, clouds, ori = prepare("/root/reference")
+    assert list(names) == list(gold["names"]) and int((ori < 8192).sum()) == 15
+    model = DH3D(full_config())
+    load_reference_checkpoint(model, os.path.join(REF, "local", "localmodel"), os.path.join(REF, "global", "globalmodel"))
+    params = {k: v.detach().numpy() for k, v in model.named_parameters()}
+    padded = int(np.nonzero(ori < 8192)[0][0])
+    for i in (0, padded, 99):
+        d = net.forward(clouds[i:i + 1], params)["globaldesc"][0]
+        assert np.abs(d - gpu[i]).max() < 5e-5, i

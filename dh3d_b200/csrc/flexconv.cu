@@ -9,6 +9,8 @@
 // one contiguous Din-float row in point-major layout, read with 16-byte loads) followed by ONE
 // dense GEMM in which K no longer appears (flops 9*N*K*Din*Dout -> 8*N*K*Din + 8*N*Din*Dout).
 // The GEMM + feature-bias/BatchNorm/ReLU epilogue is gemm_simt.cu / gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dh3d {
@@ -19,6 +21,20 @@ int linear_tc_launch(const float* x, int ldx, const void* packed, const float* s
                      int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
 size_t linear_prepack_bytes(int K, int N);
 bool gemm_use_tc();
+int flexconv_fused_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
+                          const float* scale, const float* shift, int act, float* out, int rows,
+                          int n_per_cloud, int K, int Din, int Dout, cudaStream_t st);
+bool flexconv_fused_supported(int Din, int Dout);
+
+// DH3D_FLEXCONV=split keeps the two-kernel form (moments to HBM, then the GEMM); default is the fused
+// gather -> moments -> tcgen05 kernel of flexconv_tc.cu whenever the tensor-core path is on.
+static bool flexconv_use_fused() {
+  static const bool f = [] {
+    const char* e = getenv("DH3D_FLEXCONV");
+    return !(e && (e[0] == 's' || e[0] == 'S'));
+  }();
+  return f;
+}
 int transpose_launch(const void* src, void* dst, int B, int R, int C, cudaStream_t st);
 int transpose_strided_launch(const void* src, long long sbs, int lds, void* dst, long long sbd,
                              int ldd, int B, int R, int C, cudaStream_t st);
@@ -163,6 +179,10 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
   }
 
   const long long rows = (long long)B * N;
+  if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
+  if (tc && flexconv_use_fused() && flexconv_fused_supported(Din, Dout))
+    return flexconv_fused_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
+                                 Dout, st);
   long long blocks = (rows * (Din / 4) + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   flexconv_moments_kernel<<<(int)blocks, 256, 0, st>>>(feat, xyz, nbr, A, rows, N, K, Din);

@@ -20,18 +20,13 @@
 //   warps 6-9 : epilogue of tile i overlaps the MMAs of tile i+1: tcgen05.ld (32 lanes x 32 columns
 //               per warp) -> scale/shift/act -> swizzled smem staging -> TMA store (coalesced, clips
 //               the M/N tails), or the fused row-dot kept in a register per row across the N tiles.
-#include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dh3d {
 
-constexpr int kTcBM = 128;
-constexpr int kTcBK = 32;  // fp32 elements per K slab = 128 bytes = one swizzle-128B row
 constexpr int kTcThreads = 320;
-constexpr uint32_t kTcABytes = kTcBM * kTcBK * 4;
-constexpr uint32_t kTcStageOutBytes = 4 * 32 * 32 * 4;  // 4 epilogue warps x [32 x 32] fp32
 
 template <int BN>
 struct TcCfg {
@@ -43,91 +38,6 @@ struct TcCfg {
       kStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
-      "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                               uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
-      "r"(c1), "h"(mask)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows 128 B apart, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address  [0,14)
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
-  return d;
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-
-// fp32 -> nearest tf32-representable fp32 (low 13 mantissa bits zero)
-__device__ __forceinline__ float tf32_rn(float v) {
-  uint32_t b;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
-  return __uint_as_float(b & 0xFFFFE000u);
-}
-
-__device__ __forceinline__ float tc_act(float v, int act) {
-  if (act == DH3D_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == DH3D_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-  return v;
-}
 
 struct TcEpilogue {
   const float* scale;   // [N] or null
@@ -409,49 +319,6 @@ int linear_prepack_launch(const float* w, int K, int N, void* packed, cudaStream
   if (blocks > 148 * 8) blocks = 148 * 8;
   linear_prepack_kernel<<<(int)blocks, 256, 0, st>>>(w, K, N, hi, lo);
   return launch_status();
-}
-
-// ---- host: tensor maps + launch -----------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [box_rows x 32 cols], 128B swizzle.
-static int make_map(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld,
-                    int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return DH3D_ERR_UNSUPPORTED;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? DH3D_OK : DH3D_ERR_UNSUPPORTED;
-}
-
-static int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return kNumSMs;
-    return v;
-  }();
-  return n;
 }
 
 static bool tc_use_multicast() {

@@ -170,31 +170,65 @@ flexconv_tc_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_const
             for (int p = 0; p < 4; ++p)
 #pragma unroll
               for (int c = 0; c < 8; ++c) m[h][p][c] = 0.f;
+          // The gather is latency-bound (index -> neighbour row are dependent L2 round trips), so the
+          // indices of 8 neighbours x 2 rows are fetched first, then neighbour rows are loaded two
+          // neighbours x two rows at a time (20 independent loads in flight per thread).
+          const int coff = cg * kTcBK + seg * 8;
+          long long cloud0[2];
+          float pxyz[2][3];
+          bool rv[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int row = m0 + r0 + h * 64;
-            if (row < a.rows) {
-              const long long cloud0 = (long long)(row / a.n_per_cloud) * a.n_per_cloud;
-              const float px = __ldg(a.xyz + (long long)row * 3), py = __ldg(a.xyz + (long long)row * 3 + 1),
-                          pz = __ldg(a.xyz + (long long)row * 3 + 2);
-              const int32_t* nb = a.nbr + (long long)row * a.K;
-              const int coff = cg * kTcBK + seg * 8;
-#pragma unroll 2
-              for (int k = 0; k < a.K; ++k) {
-                const long long g = cloud0 + __ldg(nb + k);
-                const float* f = a.feat + g * a.Din + coff;
-                const float4 f0 = ldg4(f), f1 = ldg4(f + 4);
-                const float dx = __ldg(a.xyz + g * 3) - px, dy = __ldg(a.xyz + g * 3 + 1) - py,
-                            dz = __ldg(a.xyz + g * 3 + 2) - pz;
-                const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            rv[h] = row < a.rows;
+            const int rr = rv[h] ? row : 0;
+            cloud0[h] = (long long)(rr / a.n_per_cloud) * a.n_per_cloud;
+            pxyz[h][0] = __ldg(a.xyz + (long long)rr * 3);
+            pxyz[h][1] = __ldg(a.xyz + (long long)rr * 3 + 1);
+            pxyz[h][2] = __ldg(a.xyz + (long long)rr * 3 + 2);
+          }
+          for (int k8 = 0; k8 < a.K; k8 += 8) {
+            int g[2][8];  // global row of the neighbour (rows < 2^31), -1 = none
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  m[h][0][c] += fv[c];
-                  m[h][1][c] = fmaf(dx, fv[c], m[h][1][c]);
-                  m[h][2][c] = fmaf(dy, fv[c], m[h][2][c]);
-                  m[h][3][c] = fmaf(dz, fv[c], m[h][3][c]);
+            for (int h = 0; h < 2; ++h) {
+              const int rr = rv[h] ? (m0 + r0 + h * 64) : 0;
+              const int32_t* nb = a.nbr + (long long)rr * a.K + k8;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) g[h][k] = (k8 + k < a.K) ? (int)cloud0[h] + __ldg(nb + k) : -1;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 2) {
+              float4 f0[2][2], f1[2][2];
+              float d[2][2][3];
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int gg = g[h][kk + u];
+                  const bool ok = rv[h] && gg >= 0;
+                  const long long gs = ok ? gg : 0;
+                  const float* f = a.feat + gs * a.Din + coff;
+                  f0[h][u] = ldg4(f);
+                  f1[h][u] = ldg4(f + 4);
+                  d[h][u][0] = __ldg(a.xyz + gs * 3) - pxyz[h][0];
+                  d[h][u][1] = __ldg(a.xyz + gs * 3 + 1) - pxyz[h][1];
+                  d[h][u][2] = __ldg(a.xyz + gs * 3 + 2) - pxyz[h][2];
+                  if (!ok) { f0[h][u] = make_float4(0.f, 0.f, 0.f, 0.f); f1[h][u] = f0[h][u]; }
                 }
-              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float fv[8] = {f0[h][u].x, f0[h][u].y, f0[h][u].z, f0[h][u].w,
+                                       f1[h][u].x, f1[h][u].y, f1[h][u].z, f1[h][u].w};
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    m[h][0][c] += fv[c];
+                    m[h][1][c] = fmaf(d[h][u][0], fv[c], m[h][1][c]);
+                    m[h][2][c] = fmaf(d[h][u][1], fv[c], m[h][2][c]);
+                    m[h][3][c] = fmaf(d[h][u][2], fv[c], m[h][3][c]);
+                  }
+                }
             }
           }
           // 4 K-slabs (p' = 1, x, y, z) -> 4 consecutive stages, swizzled K-major, hi (raw) + lo

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "dh3d_query_ball_point": (_c_int, [_c_int, _c_int, _c_int, _c_float, _c_int, _p, _p, _p, _p, _p,
                                        _c_size_t, _p]),
     "dh3d_three_nn": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p]),
+    "dh3d_three_nn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "dh3d_three_nn_ws": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _c_size_t, _p]),
     "dh3d_three_interpolate": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_three_interpolate_from_dist": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_linear": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p]),
@@ -64,7 +66,7 @@ _KERNELS_PER_CALL = {
     "dh3d_knn_bruteforce": 2, "dh3d_knn_bruteforce_pm": 2,          # pack + scan
     "dh3d_flex_conv": 8,                                             # 4 transposes + theta_ext + moments + gemm (+memset)
     "dh3d_flex_conv_pm": 3,                                          # theta_ext + moments + gemm (+1 if feature_bias)
-    "dh3d_query_ball_point": 2, "dh3d_netvlad": 4,
+    "dh3d_query_ball_point": 2, "dh3d_netvlad": 4, "dh3d_three_nn_ws": 3,
 }
 
 

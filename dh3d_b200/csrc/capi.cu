@@ -26,6 +26,9 @@ int conv_pointset_cm_launch(const float* feat, const float* theta, const float* 
                             cudaStream_t st);
 int three_nn_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
                     int32_t* idx, cudaStream_t st);
+size_t three_nn_workspace_bytes(int b, int n, int m);
+int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                           int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int three_interpolate_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
                              const float* wsrc, float* out, bool from_dist, cudaStream_t st);
 size_t query_ball_workspace_bytes(int b, int m);
@@ -52,6 +55,14 @@ int linear_tc_launch(const float* x, int ldx, const void* packed, const float* s
 int linear_rowdot_tc_launch(const float* x, int ldx, const void* packed, const float* scale,
                             const float* shift, int act, const float* w2, float b2, int act2, float* y2,
                             int M, int K, int N, cudaStream_t st);
+// gemm_tc16.cu
+size_t linear_prepack16_bytes(int K, int N);
+int linear_prepack16_launch(const float* w, int K, int N, void* packed, cudaStream_t st);
+int linear_tc16_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
+                       int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
+int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const float* scale,
+                              const float* shift, int act, const float* w2, float b2, int act2, float* y2,
+                              int M, int K, int N, cudaStream_t st);
 // flexconv.cu
 size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout);
 size_t flex_conv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
@@ -80,6 +91,16 @@ bool gemm_use_tc() {
     return !(e && (e[0] == 's' || e[0] == 'S'));
   }();
   return tc;
+}
+
+// Split used by the packed dense layers (dh3d_linear_prepack / _packed / _rowdot_packed; process-wide,
+// read once): default fp16 pairs on kind::f16 (gemm_tc16.cu); DH3D_GEMM_SPLIT=tf32 -> gemm_tc.cu.
+bool gemm_split_f16() {
+  static const bool f16 = [] {
+    const char* e = getenv("DH3D_GEMM_SPLIT");
+    return !(e && (e[0] == 't' || e[0] == 'T'));
+  }();
+  return f16;
 }
 
 // GEMM dispatch (one place to switch the dense path)
@@ -190,6 +211,11 @@ int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, flo
                   int32_t* idx, void* stream) {
   return three_nn_launch(b, n, m, xyz1, xyz2, dist, idx, S(stream));
 }
+size_t dh3d_three_nn_workspace_bytes(int b, int n, int m) { return three_nn_workspace_bytes(b, n, m); }
+int dh3d_three_nn_ws(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                     int32_t* idx, void* workspace, size_t workspace_bytes, void* stream) {
+  return three_nn_pruned_launch(b, n, m, xyz1, xyz2, dist, idx, workspace, workspace_bytes, S(stream));
+}
 int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
                            const float* weight, float* out, void* stream) {
   return three_interpolate_launch(b, m, c, n, points, idx, weight, out, false, S(stream));
@@ -204,18 +230,27 @@ int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, con
                 int act, float* y, int ldy, int M, int K, int N, void* stream) {
   return linear_launch(x, ldx, w, scale, shift, act, y, ldy, M, K, N, S(stream));
 }
-size_t dh3d_linear_prepack_bytes(int K, int N) { return linear_prepack_bytes(K, N); }
+size_t dh3d_linear_prepack_bytes(int K, int N) {
+  const size_t a = linear_prepack_bytes(K, N), b = linear_prepack16_bytes(K, N);
+  return a > b ? a : b;  // either format fits
+}
 int dh3d_linear_prepack(const float* w, int K, int N, void* packed, void* stream) {
+  if (gemm_split_f16()) return linear_prepack16_launch(w, K, N, packed, S(stream));
   return linear_prepack_launch(w, K, N, packed, S(stream));
 }
 int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        void* stream) {
+  if (gemm_split_f16())
+    return linear_tc16_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
   return linear_tc_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
 }
 int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                               const float* shift, int act, const float* w2, float b2, int act2,
                               float* y, int M, int K, int N, void* stream) {
+  if (gemm_split_f16())
+    return linear_rowdot_tc16_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N,
+                                     S(stream));
   return linear_rowdot_tc_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
 }
 int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,

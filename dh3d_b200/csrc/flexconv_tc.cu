@@ -56,7 +56,8 @@ flexconv_tc_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_const
   using Cfg = FcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment computed on the shared-window address so the pointer keeps its state space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* out_stage = smem + S * Cfg::kStageBytes;
   float* params = reinterpret_cast<float*>(out_stage + kTcStageOutBytes);  // [2][2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);

@@ -189,6 +189,65 @@ conv_pointset_kernel(const float* __restrict__ feat, const float* __restrict__ t
   }
 }
 
+// DH3D's own shape (xyz features, K = 8, Dout = 32): 8 lanes per point.  Lane s of a group gathers
+// neighbour s (one coalesced 32-byte index row, 8 independent 12-byte gathers in flight per point) and
+// owns output channels 4s..4s+3 with their 12 theta values in registers; the reference's (k outer,
+// c inner) FMA chain runs on width-8 shuffles; the output row leaves as 8 float4 = 128 contiguous bytes.
+__global__ void __launch_bounds__(256)
+conv_pointset_k8c3o32_kernel(const float* __restrict__ feat, const float* __restrict__ theta,
+                             const float* __restrict__ bias, const int32_t* __restrict__ nbr,
+                             float* __restrict__ out, long long rows, int n,
+                             const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+  const int sub = threadIdx.x & 7;
+  float th[3][4], bs[4], sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = sub * 4 + j;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) th[c][j] = __ldg(theta + c * 32 + o);
+    bs[j] = __ldg(bias + o);
+    sc[j] = scale ? __ldg(scale + o) : 1.f;
+    sh[j] = shift ? __ldg(shift + o) : 0.f;
+  }
+  const long long stride = ((long long)gridDim.x * blockDim.x) >> 3;
+  const long long first = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long iters = (rows + stride - 1) / stride;  // same trip count for every lane of a warp
+  for (long long it = 0; it < iters; ++it) {
+    const long long r = first + it * stride;
+    const bool valid = r < rows;
+    const long long rr = valid ? r : rows - 1;
+    const long long b = rr / n;
+    const int g = __ldg(nbr + rr * 8 + sub);
+    const float* p = feat + (b * n + g) * 3;
+    const float fx = __ldg(p), fy = __ldg(p + 1), fz = __ldg(p + 2);
+    const float dx = __fsub_rn(fx, __shfl_sync(0xffffffffu, fx, 0, 8));
+    const float dy = __fsub_rn(fy, __shfl_sync(0xffffffffu, fy, 0, 8));
+    const float dz = __fsub_rn(fz, __shfl_sync(0xffffffffu, fz, 0, 8));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const float vx = __shfl_sync(0xffffffffu, dx, kk, 8);
+      const float vy = __shfl_sync(0xffffffffu, dy, kk, 8);
+      const float vz = __shfl_sync(0xffffffffu, dz, kk, 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j] = __fmaf_rn(th[0][j], vx, acc[j]);
+        acc[j] = __fmaf_rn(th[1][j], vy, acc[j]);
+        acc[j] = __fmaf_rn(th[2][j], vz, acc[j]);
+      }
+    }
+    float o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = __fadd_rn(acc[j], bs[j]);
+      if (scale) a *= sc[j];
+      if (shift) a += sh[j];
+      o4[j] = apply_act(a, act);
+    }
+    if (valid) *reinterpret_cast<float4*>(out + r * 32 + sub * 4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
+
 int conv_pointset_pm_launch(const float* feat, const float* theta, const float* bias,
                             const int32_t* nbr, float* out, int B, int N, int K, int Din, int Dout,
                             const float* scale, const float* shift, int act, cudaStream_t st) {
@@ -196,6 +255,11 @@ int conv_pointset_pm_launch(const float* feat, const float* theta, const float* 
   if (B <= 0 || N <= 0 || K <= 0 || Din <= 0 || Dout <= 0) return DH3D_ERR_DIM;
   if (Din > 64 || (size_t)Din * Dout * sizeof(float) > 48 * 1024) return DH3D_ERR_UNSUPPORTED;
   const long long rows = (long long)B * N;
+  if (K == 8 && Din == 3 && Dout == 32 && (((uintptr_t)out) & 15) == 0) {
+    conv_pointset_k8c3o32_kernel<<<ew_blocks(rows * 8, 256), 256, 0, st>>>(feat, theta, bias, nbr, out, rows,
+                                                                          N, scale, shift, act);
+    return launch_status();
+  }
   conv_pointset_kernel<<<ew_blocks(rows * 32, 256), 256, (size_t)Din * Dout * sizeof(float), st>>>(
       feat, theta, bias, nbr, out, rows, N, K, Din, Dout, scale, shift, act);
   return launch_status();

@@ -1,0 +1,501 @@
+// Dense 1x1 layers on the fp16 tensor-core path with fp32-grade accuracy:  Y = act((X @ W) * scale + shift)
+//   optionally fused with a following 1-column layer:  y[m] = act2( sum_n Y[m,n] * w2[n] + b2 )
+//
+// tcgen05.mma kind::f16 runs at twice the kind::tf32 rate, and a 2-term fp16 split carries 22 mantissa
+// bits just like the tf32 split of gemm_tc.cu, so the same 3 MMAs per product cost half the time:
+//     x' = x * 2^4          = xh + xl      (xh = fp16(x'), xl = fp16(x' - xh))
+//     w' = w * sw[n]        = wh + wl      (sw[n] = power of two putting max_k |w[k,n]| in [2^13, 2^14))
+//     x'*w' ~= xl*wh + xh*wl + xh*wh       (dropped xl*wl ~ 2^-22 relative), result * 2^-4 / sw[n]
+// fp16 has 5 exponent bits, hence the scaling: the low parts stay normal (or lose at most 2^-25
+// absolute = 2^-29 of |x| = 1) for activations with |x| in [2^-12, 4094]; an activation beyond that
+// converts to inf and the output row turns inf/NaN (loud, never silently wrong).  Weight columns are
+// scaled individually, so any weight magnitude works.  DH3D_GEMM_SPLIT=tf32 selects gemm_tc.cu instead.
+//
+// Same persistent warp-specialised structure as gemm_tc.cu (320 threads, one CTA per SM, 2-CTA
+// clusters multicasting the W tiles), with
+//   * K slabs of 32: raw X tile [128 x 32] fp32 (TMA, 128B swizzle) -> warps 2-5 write xh / xl as
+//     [128 x 32] fp16 tiles in the 64B-swizzled K-major layout (conflict-free 16-byte loads/stores);
+//     W_h^T / W_l^T tiles [BN x 32] fp16 arrive by TMA in that layout (pre-split once per weight);
+//   * BN up to 256 (two 256-column TMEM accumulators = all 512 columns), which halves how often
+//     the X tile is re-streamed and re-split for wide layers (256 -> 1024 heads: 4 N tiles);
+//   * 2 (k) x 3 (split terms) tcgen05.mma 128 x BN x 16 per slab.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace dh3d {
+
+constexpr int kT16Threads = 320;
+constexpr float kT16XScale = 16.f;         // 2^4
+constexpr float kT16XScaleInv = 0.0625f;
+
+template <int BN>
+struct T16Cfg {
+  static constexpr int kStages = BN >= 256 ? 3 : 4;
+  static constexpr uint32_t kRawBytes = kTcBM * kTcBK * 4;   // 16 KB fp32, SW128
+  static constexpr uint32_t kABytes = kTcBM * kTcBK * 2;     // 8 KB fp16, SW64
+  static constexpr uint32_t kBBytes = BN * kTcBK * 2;
+  static constexpr uint32_t kStageBytes = kRawBytes + 2 * kABytes + 2 * kBBytes;
+  static constexpr uint32_t kParamBytes = 2 * 3 * BN * 4;    // double-buffered scale/shift/w2 slices
+  static constexpr uint32_t kSmemBytes =
+      kStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+struct T16Epilogue {
+  const float* scale;     // [N] or null
+  const float* shift;     // [N] or null
+  const float* colscale;  // [N]: 2^-4 / sw[n] (from the prepack)
+  int act;
+  const float* w2;        // [N]: fused row-dot (ROWDOT mode)
+  float b2;
+  int act2;
+  float* y2;              // [M]   (ROWDOT mode)
+};
+
+// K-major, 64B-swizzled operand tile: rows 64 B apart, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address  [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                        // layout type SWIZZLE_64B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 8 consecutive fp32 -> 8 fp16 high parts + 8 fp16 low parts (of x * 2^4), packed as two uint4
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float v[8] = {a.x * kT16XScale, a.y * kT16XScale, a.z * kT16XScale, a.w * kT16XScale,
+                      b.x * kT16XScale, b.y * kT16XScale, b.z * kT16XScale, b.w * kT16XScale};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int BN, bool ROWDOT, int MC>
+__global__ void __launch_bounds__(kT16Threads, 1)
+gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                 const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmY,
+                 const T16Epilogue ep, int M, int K, int N) {
+  using Cfg = T16Cfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment computed on the shared-window address so the pointer keeps its state space (LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* out_stage = smem + S * Cfg::kStageBytes;                       // 4 x 4 KB, 1024-aligned
+  float* params = reinterpret_cast<float*>(out_stage + kTcStageOutBytes);  // [2][3][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);
+  uint64_t* full = bars;            // TMA bytes landed                 (count 1 + tx)
+  uint64_t* conv = bars + S;        // xh / xl written                  (count 128)
+  uint64_t* empty = bars + 2 * S;   // MMAs reading the stage finished  (count MC, tcgen05.commit)
+  uint64_t* tmem_full = bars + 3 * S;       // [2] accumulator ready    (count 1, tcgen05.commit)
+  uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] accumulator drained  (count 4, one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (K + kTcBK - 1) / kTcBK;
+  const int num_mt = (M + kTcBM - 1) / kTcBM;
+  const int num_nt = (N + BN - 1) / BN;
+  const uint32_t crank = MC > 1 ? cluster_ctarank() : 0;
+  const int mt_begin = (int)(blockIdx.x / MC) * MC;  // first tile of this cluster
+  const int mt_stride = (int)gridDim.x;
+
+  auto stage_raw = [&](int s) { return smem + s * Cfg::kStageBytes; };
+  auto stage_ah = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes; };
+  auto stage_al = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + Cfg::kABytes; };
+  auto stage_bh = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes; };
+  auto stage_bl = [&](int s) {
+    return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes + Cfg::kBBytes;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], MC);  // one tcgen05.commit per CTA of the cluster (peers write this stage too)
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride) {
+        const int mt = mtb + (int)crank;
+        for (int nt = 0; nt < num_nt; ++nt)
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], Cfg::kRawBytes + 2 * Cfg::kBBytes);
+            tma_load_2d(stage_raw(s), &tmA, kb * kTcBK, mt * kTcBM, &full[s]);
+            if constexpr (MC == 1) {
+              tma_load_2d(stage_bh(s), &tmBh, kb * kTcBK, nt * BN, &full[s]);
+              tma_load_2d(stage_bl(s), &tmBl, kb * kTcBK, nt * BN, &full[s]);
+            } else {
+              // this CTA's half of the W tile (rows crank*BN/2 ..) lands in BOTH CTAs' stage s
+              constexpr int HB = BN / MC;
+              const uint32_t off = crank * HB * (kTcBK * 2);
+              tma_load_2d_mc(stage_bh(s) + off, &tmBh, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
+                             (uint16_t)((1u << MC) - 1));
+              tma_load_2d_mc(stage_bl(s) + off, &tmBl, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
+                             (uint16_t)((1u << MC) - 1));
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      uint32_t it = 0, tile = 0;
+      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
+        for (int nt = 0; nt < num_nt; ++nt, ++tile) {
+          const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
+          mbar_wait(&tmem_empty[acc], aph ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(&conv[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_h = umma_desc_sw64(smem_u32(stage_ah(s)));
+            const uint64_t a_l = umma_desc_sw64(smem_u32(stage_al(s)));
+            const uint64_t b_h = umma_desc_sw64(smem_u32(stage_bh(s)));
+            const uint64_t b_l = umma_desc_sw64(smem_u32(stage_bl(s)));
+#pragma unroll
+            for (int k = 0; k < kTcBK / 16; ++k) {
+              const uint64_t off = (uint64_t)(k * 16 * 2) >> 4;  // 32 bytes per K=16 step, 16-byte units
+              umma_f16(tmem_d, a_l + off, b_h + off, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_d, a_h + off, b_l + off, idesc, 1u);
+              umma_f16(tmem_d, a_h + off, b_h + off, idesc, 1u);
+            }
+            if constexpr (MC == 1) umma_commit(&empty[s]);
+            else umma_commit_mc(&empty[s], (uint16_t)((1u << MC) - 1));  // frees the stage in every CTA
+          }
+          umma_commit(&tmem_full[acc]);
+        }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ fp32 -> (xh, xl) fp16 split
+    // task = (row, 16-byte destination chunk of 8 K values); thread t: chunk t&3 of rows (t>>2) + 32*i.
+    // A quarter-warp touches 2 rows x 4 chunks: 8 distinct 16-byte columns of the 128B-swizzled source
+    // and 128 contiguous bytes of the 64B-swizzled destination, so no access is bank-conflicted.
+    const int t = threadIdx.x - 64;  // 0..127
+    const int c = t & 3;
+    uint32_t it = 0;
+    for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
+      for (int nt = 0; nt < num_nt; ++nt)
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(&full[s], ph);
+          const uint8_t* raw = stage_raw(s);
+          uint8_t* ah = stage_ah(s);
+          uint8_t* al = stage_al(s);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (t >> 2) + 32 * i;
+            const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
+            const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
+            uint4 hi, lo;
+            split8(v0, v1, hi, lo);
+            const uint32_t off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(ah + off) = hi;
+            *reinterpret_cast<uint4*>(al + off) = lo;
+          }
+          fence_proxy_async();
+          mbar_arrive(&conv[s]);
+        }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 6..9)
+    const int q = warp & 3;              // TMEM lane quadrant of this warp
+    const int et = threadIdx.x - 192;    // 0..127
+    uint8_t* my_stage = out_stage + (warp - 6) * 4096;
+    uint32_t tile = 0;
+    for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride) {
+      const int mt = mtb + (int)crank;
+      float dot = 0.f;
+      for (int nt = 0; nt < num_nt; ++nt, ++tile) {
+        const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
+        float* prm = params + acc * 3 * BN;
+        // per-tile epilogue constants -> smem (double-buffered with the accumulator index)
+        for (int cc = et; cc < BN; cc += 128) {
+          const int gc = nt * BN + cc;
+          const bool in = gc < N;
+          const float cs = in ? __ldg(ep.colscale + gc) : 0.f;
+          prm[cc] = ((in && ep.scale) ? __ldg(ep.scale + gc) : 1.f) * cs;
+          prm[BN + cc] = (in && ep.shift) ? __ldg(ep.shift + gc) : 0.f;
+          prm[2 * BN + cc] = (ROWDOT && in) ? __ldg(ep.w2 + gc) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(&tmem_full[acc], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          DH3D_TMEM_LD_32X32(r, taddr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 32 >= BN) {  // accumulator fully read: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            v[j] = tc_act(fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]), ep.act);
+          if constexpr (ROWDOT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(v[j], prm[2 * BN + c0 + j], dot);
+          } else {
+            if (nt * BN + c0 < N) {
+              // staging tile [32 rows x 128 B], 128B-swizzled like the tensor map expects
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmY, my_stage, nt * BN + c0, mt * kTcBM + q * 32);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // params[acc] may be rewritten two tiles later
+      }
+      if constexpr (ROWDOT) {
+        const int row = mt * kTcBM + q * 32 + lane;
+        if (row < M) ep.y2[row] = tc_act(dot + ep.b2, ep.act2);
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- weight pre-split: W [K,N] row-major -> { W_h^T [N,Kp] fp16, W_l^T [N,Kp] fp16, colscale [N] } --------
+// one CTA per output column n; Kp = K rounded up to 8 (16-byte row pitch for the tensor map), zero padded
+__global__ void __launch_bounds__(256)
+linear_prepack16_kernel(const float* __restrict__ w, int K, int Kp, int N, __half* __restrict__ hi,
+                        __half* __restrict__ lo, float* __restrict__ colscale) {
+  __shared__ float s_red[8];
+  __shared__ float s_sw;
+  const int n = blockIdx.x;
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, fabsf(w[(long long)k * N + n]));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, s_red[i]);
+    float sw = 1.f;
+    if (m > 0.f && m < CUDART_INF_F) {
+      int e;
+      frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+      sw = ldexpf(1.f, 14 - e);  // m * sw in [2^13, 2^14)
+    }
+    s_sw = sw;
+    colscale[n] = kT16XScaleInv / sw;
+  }
+  __syncthreads();
+  const float sw = s_sw;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    const float v = k < K ? w[(long long)k * N + n] * sw : 0.f;
+    const __half h = __float2half_rn(v);
+    hi[(long long)n * Kp + k] = h;
+    lo[(long long)n * Kp + k] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+static inline int t16_kp(int K) { return (K + 7) / 8 * 8; }
+static inline size_t t16_plane_bytes(int K, int N) { return align_up((size_t)t16_kp(K) * N * sizeof(__half), 256); }
+
+size_t linear_prepack16_bytes(int K, int N) {
+  if (K <= 0 || N <= 0) return 0;
+  return 2 * t16_plane_bytes(K, N) + align_up((size_t)N * sizeof(float), 256);
+}
+
+int linear_prepack16_launch(const float* w, int K, int N, void* packed, cudaStream_t st) {
+  if (!w || !packed) return DH3D_ERR_NULL;
+  if (K <= 0 || N <= 0) return DH3D_ERR_DIM;
+  if (K % 4 || N % 4) return DH3D_ERR_DIM;
+  if (((uintptr_t)packed & 255) != 0) return DH3D_ERR_ALIGN;
+  char* base = reinterpret_cast<char*>(packed);
+  __half* hi = reinterpret_cast<__half*>(base);
+  __half* lo = reinterpret_cast<__half*>(base + t16_plane_bytes(K, N));
+  float* cs = reinterpret_cast<float*>(base + 2 * t16_plane_bytes(K, N));
+  linear_prepack16_kernel<<<N, 256, 0, st>>>(w, K, t16_kp(K), N, hi, lo, cs);
+  return launch_status();
+}
+
+// 2-D fp16 tensor [rows, cols] with row pitch ld (elements); box = [box_rows x 32 cols], 64B swizzle.
+static int make_map_f16(CUtensorMap* m, const __half* base, long long rows, long long cols, long long ld,
+                        int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return DH3D_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DH3D_OK : DH3D_ERR_UNSUPPORTED;
+}
+
+static bool t16_use_multicast() {
+  static const bool on = [] {
+    const char* e = getenv("DH3D_GEMM_MULTICAST");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int BN, bool ROWDOT, int MC>
+static int launch_t16_mc(const float* x, int ldx, const __half* wh, const __half* wl, const T16Epilogue& ep,
+                         float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+  CUtensorMap ma, mh, ml, my;
+  int rc;
+  const int Kp = t16_kp(K);
+  if ((rc = make_map(&ma, x, M, K, ldx, kTcBM)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&mh, wh, N, Kp, Kp, BN / MC)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&ml, wl, N, Kp, Kp, BN / MC)) != DH3D_OK) return rc;
+  if (ROWDOT) my = ma;
+  else if ((rc = make_map(&my, y, M, N, ldy, 32)) != DH3D_OK) return rc;
+  auto kern = gemm_tc16_kernel<BN, ROWDOT, MC>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)T16Cfg<BN>::kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  const int num_mt = ceil_div(M, kTcBM);
+  int grid = num_mt < num_sms() ? num_mt : num_sms();
+  grid = ceil_div(grid, MC) * MC;
+  if (grid > num_sms()) grid -= MC;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kT16Threads);
+  cfg.dynamicSmemBytes = T16Cfg<BN>::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, ma, mh, ml, my, ep, M, K, N);
+  if (e != cudaSuccess) return (int)e;
+  return launch_status();
+}
+
+template <int BN, bool ROWDOT>
+static int launch_t16(const float* x, int ldx, const __half* wh, const __half* wl, const T16Epilogue& ep,
+                      float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+  // pairs of CTAs share each W tile when there are enough M tiles to pair up and W is re-streamed
+  if (BN >= 64 && t16_use_multicast() && ceil_div(M, kTcBM) >= 2 * 16)
+    return launch_t16_mc<BN, ROWDOT, 2>(x, ldx, wh, wl, ep, y, ldy, M, K, N, st);
+  return launch_t16_mc<BN, ROWDOT, 1>(x, ldx, wh, wl, ep, y, ldy, M, K, N, st);
+}
+
+static int t16_check(const float* x, int ldx, const void* packed, int M, int K, int N) {
+  if (!x || !packed) return DH3D_ERR_NULL;
+  if (M <= 0 || K <= 0 || N <= 0) return DH3D_ERR_DIM;
+  if (K % 4 || N % 4 || ldx % 4 || ldx < K) return DH3D_ERR_DIM;
+  if ((((uintptr_t)x | (uintptr_t)packed) & 15) != 0) return DH3D_ERR_ALIGN;
+  return DH3D_OK;
+}
+
+struct T16Packed { const __half* wh; const __half* wl; const float* cs; };
+static inline T16Packed t16_unpack(const void* packed, int K, int N) {
+  const char* base = reinterpret_cast<const char*>(packed);
+  T16Packed p;
+  p.wh = reinterpret_cast<const __half*>(base);
+  p.wl = reinterpret_cast<const __half*>(base + t16_plane_bytes(K, N));
+  p.cs = reinterpret_cast<const float*>(base + 2 * t16_plane_bytes(K, N));
+  return p;
+}
+
+int linear_tc16_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
+                       int act, float* y, int ldy, int M, int K, int N, cudaStream_t st) {
+  int rc = t16_check(x, ldx, packed, M, K, N);
+  if (rc != DH3D_OK) return rc;
+  if (!y) return DH3D_ERR_NULL;
+  if (ldy % 4 || ldy < N) return DH3D_ERR_DIM;
+  if ((((uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return DH3D_ERR_ALIGN;
+  const T16Packed p = t16_unpack(packed, K, N);
+  T16Epilogue ep{scale, shift, p.cs, act, nullptr, 0.f, 0, nullptr};
+  if (N <= 32) return launch_t16<32, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
+  if (N <= 64) return launch_t16<64, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
+  if (N <= 128) return launch_t16<128, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
+  return launch_t16<256, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
+}
+
+int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const float* scale,
+                              const float* shift, int act, const float* w2, float b2, int act2, float* y2,
+                              int M, int K, int N, cudaStream_t st) {
+  int rc = t16_check(x, ldx, packed, M, K, N);
+  if (rc != DH3D_OK) return rc;
+  if (!w2 || !y2) return DH3D_ERR_NULL;
+  const T16Packed p = t16_unpack(packed, K, N);
+  T16Epilogue ep{scale, shift, p.cs, act, w2, b2, act2, y2};
+  if (N <= 64) return launch_t16<64, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
+  if (N <= 128) return launch_t16<128, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
+  return launch_t16<256, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
+}
+
+}  // namespace dh3d

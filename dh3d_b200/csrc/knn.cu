@@ -228,98 +228,191 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
 // ---------------------------------------------------------------------------------------------
 // query
 // ---------------------------------------------------------------------------------------------
-// KC = compiled list length (>= K).  EXACT: K == KC and outputs are 16-byte aligned.
-template <int KC, bool EXACT>
+// Distance policies.  d2() is the exact operation sequence of the reference, key() the sort key,
+// bound() a value such that every candidate whose key could still enter the list has d2 <= bound.
+struct KnnMetric {      // knn_bruteforce_kernel_gpu.cu.cc:102-107 (nvcc-contracted), key = sqrt.rn
+  static __device__ __forceinline__ float d2(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  }
+  static __device__ __forceinline__ float key(float d) { return __fsqrt_rn(d); }
+  // every d2 with sqrt.rn(d2) <= k satisfies d2 <= k^2*(1+2^-23) < the bound below
+  static __device__ __forceinline__ float bound(float k) { return __fmul_rn(__fmul_rn(k, k), 1.000001f); }
+  static __device__ __forceinline__ int rank_of(int x, int T, int logT, int logV) {
+    return knn_rank_of(x, T, logT, logV);
+  }
+  static __device__ __forceinline__ int point_of(int r, int T, int logV) { return knn_point_of(r, T, logV); }
+  static constexpr uint32_t kInitKey = 0x7f7fffffu;  // FLT_MAX, the reference's padding key
+  static constexpr int kInitRank = INT_MAX;
+};
+struct ThreeNnMetric {  // tf_interpolate.cpp:60-103: un-fused (dx*dx + dy*dy) + dz*dz, key = d2, ties to low index
+  static __device__ __forceinline__ float d2(float dx, float dy, float dz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  }
+  static __device__ __forceinline__ float key(float d) { return d; }
+  static __device__ __forceinline__ float bound(float k) { return k; }
+  static __device__ __forceinline__ int rank_of(int x, int, int, int) { return x; }
+  static __device__ __forceinline__ int point_of(int r, int, int) { return r; }
+  static constexpr uint32_t kInitKey = 0x7f800000u;  // best = 1e40 -> +inf in float, index 0
+  static constexpr int kInitRank = 0;
+};
+
+constexpr int kKnnCap = 16;  // buffered candidates per query before a flush
+
+// One thread per query, KC-entry sorted list of packed (key bits, rank) pairs in registers.  A non-negative
+// float orders like its bit pattern, so one 64-bit integer compare is the reference's (key, tie-rank) order.
+// The scan loop never branches into the insertion: a candidate under the lane's bound is appended to the
+// lane's column of a shared-memory buffer (predicated store); the warp inserts the buffered candidates
+// together when some lane's column fills up (or at the end of a chunk), which is where the bound tightens.
+// A stale bound is only looser, so nothing is lost.  KC >= K; EXACT: K == KC and 16-byte aligned outputs.
+// SELF: queries are the candidates themselves (k-NN; the walk starts at the warp's own chunk), otherwise
+// the walk starts at the chunk whose box is nearest to the warp's first query (3-NN).
+template <int KC, bool EXACT, bool SELF, class M>
 __global__ void __launch_bounds__(kKnnThreads)
-knn_query_kernel(const float4* __restrict__ sorted, const float4* __restrict__ boxes, int N, int Np,
-                 int T, int logT, int logV, int K, int32_t* __restrict__ ids,
-                 float* __restrict__ dists) {
+knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const float4* __restrict__ sorted,
+                 const float4* __restrict__ boxes, int Np, int T, int logT, int logV, int K, int flush_min,
+                 int32_t* __restrict__ ids, float* __restrict__ dists) {
+  __shared__ float2 s_buf[kKnnCap][kKnnThreads];
   const int b = blockIdx.y;
-  const int p = blockIdx.x * kKnnThreads + threadIdx.x;  // sorted position of this thread's query
+  const int tid = threadIdx.x;
+  const int p = blockIdx.x * kKnnThreads + tid;  // sorted position of this thread's query
   const float4* cloud = sorted + (long long)b * Np;
   const float4* bx = boxes + (long long)b * (Np / kKnnChunk) * 2;
   const int nchunks = Np / kKnnChunk;
 
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int y = -1;
-  if (p < Np) {
-    const float4 q = __ldg(cloud + p);
+  if (p < Nqp) {
+    const float4 q = __ldg(qsorted + (long long)b * Nqp + p);
     y = __float_as_int(q.w);
     if (y >= 0) { qx = q.x; qy = q.y; qz = q.z; }
   }
   const bool active = y >= 0;
 
-  float sq[KC];
-  int rk[KC];
+  constexpr unsigned long long kInit = ((unsigned long long)M::kInitKey << 32) | (uint32_t)M::kInitRank;
+  unsigned long long L[KC];
 #pragma unroll
-  for (int j = 0; j < KC; ++j) { sq[j] = 3.402823466e+38f; rk[j] = INT_MAX; }  // reference padding lanes
-  float kth_s = 3.402823466e+38f;  // current K-th key ...
-  int kth_r = INT_MAX;             // ... and its rank
-  float thr2 = active ? CUDART_INF_F : -1.f;  // d^2 bound implied by kth_s (inactive lanes never pass)
+  for (int j = 0; j < KC; ++j) L[j] = kInit;
+  float thr2 = active ? CUDART_INF_F : -1.f;  // inactive lanes never pass
+  int cnt = 0;
 
-  const int c0 = min((int)((blockIdx.x * kKnnThreads + (threadIdx.x & ~31)) / kKnnChunk), nchunks - 1);
-  // walk outward: c0, c0+1, c0-1, c0+2, ...
-  for (int step = 0; step < 2 * nchunks; ++step) {
-    const int c = (step & 1) ? c0 + ((step + 1) >> 1) : c0 - (step >> 1);
-    if (c < 0 || c >= nchunks) continue;
-    const float4 lo4 = __ldg(bx + 2 * c), hi4 = __ldg(bx + 2 * c + 1);
-    // lower bound of the computed d^2 to any point in the box (same op sequence as below)
-    const float ex = fmaxf(fmaxf(lo4.x - qx, qx - hi4.x), 0.f);
-    const float ey = fmaxf(fmaxf(lo4.y - qy, qy - hi4.y), 0.f);
-    const float ez = fmaxf(fmaxf(lo4.z - qz, qz - hi4.z), 0.f);
-    const float lb = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
-    if (!__any_sync(0xffffffffu, lb <= thr2)) continue;
-    const float4* cand = cloud + c * kKnnChunk;
-#pragma unroll 8
-    for (int j = 0; j < kKnnChunk; ++j) {
-      const float4 v = __ldg(cand + j);
-      const float dx = v.x - qx, dy = v.y - qy, dz = v.z - qz;
-      const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-      if (d2 <= thr2) {
-        const float s = __fsqrt_rn(d2);
-        const int x = __float_as_int(v.w);
-        const int r = knn_rank_of(x, T, logT, logV);
-        if (x >= 0 && (s < kth_s || (s == kth_s && r < kth_r))) {
+  auto flush = [&]() {
+    int m = cnt;
 #pragma unroll
-          for (int i = KC - 1; i > 0; --i) {
-            const bool before_prev = s < sq[i - 1] || (s == sq[i - 1] && r < rk[i - 1]);
-            const bool before_here = s < sq[i] || (s == sq[i] && r < rk[i]);
-            if (before_prev) { sq[i] = sq[i - 1]; rk[i] = rk[i - 1]; }
-            else if (before_here) { sq[i] = s; rk[i] = r; }
-          }
-          if (s < sq[0] || (s == sq[0] && r < rk[0])) { sq[0] = s; rk[0] = r; }
-          if constexpr (EXACT) {
-            kth_s = sq[KC - 1]; kth_r = rk[KC - 1];
-          } else {
-            kth_s = sq[0]; kth_r = rk[0];
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int e = 0; e < m; ++e) {
+      if (e < cnt) {
+        const float2 c = s_buf[e][tid];
+        const int x = __float_as_int(c.y);
+        if (x >= 0) {
+          const unsigned long long pk = ((unsigned long long)__float_as_uint(M::key(c.x)) << 32) |
+                                        (uint32_t)M::rank_of(x, T, logT, logV);
+          unsigned long long kth = L[KC - 1];
+          if constexpr (!EXACT) {
+            kth = L[0];
 #pragma unroll
-            for (int i = 1; i < KC; ++i) { kth_s = (i < K) ? sq[i] : kth_s; kth_r = (i < K) ? rk[i] : kth_r; }
+            for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
           }
-          // every d2 with sqrt.rn(d2) <= kth_s satisfies d2 <= kth_s^2*(1+2^-23) < the bound below
-          thr2 = __fmul_rn(__fmul_rn(kth_s, kth_s), 1.000001f);
+          if (pk < kth) {
+#pragma unroll
+            for (int i = KC - 1; i > 0; --i) {
+              const bool before_prev = pk < L[i - 1];
+              const bool before_here = pk < L[i];
+              L[i] = before_prev ? L[i - 1] : (before_here ? pk : L[i]);
+            }
+            if (pk < L[0]) L[0] = pk;
+          }
         }
       }
     }
+    cnt = 0;
+    unsigned long long kth = L[KC - 1];
+    if constexpr (!EXACT) {
+      kth = L[0];
+#pragma unroll
+      for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
+    }
+    if (active) thr2 = M::bound(__uint_as_float((uint32_t)(kth >> 32)));
+  };
+
+  auto box_lb = [&](int c) -> float {
+    const float4 lo4 = __ldg(bx + 2 * c), hi4 = __ldg(bx + 2 * c + 1);
+    // lower bound of the computed d2 to any point in the box (same op sequence, monotone roundings)
+    const float ex = fmaxf(fmaxf(lo4.x - qx, qx - hi4.x), 0.f);
+    const float ey = fmaxf(fmaxf(lo4.y - qy, qy - hi4.y), 0.f);
+    const float ez = fmaxf(fmaxf(lo4.z - qz, qz - hi4.z), 0.f);
+    return M::d2(ex, ey, ez);
+  };
+
+  int c0;
+  if constexpr (SELF) {
+    c0 = min((int)((blockIdx.x * kKnnThreads + (tid & ~31)) / kKnnChunk), nchunks - 1);
+  } else {
+    float best = CUDART_INF_F;
+    int bc = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      const float lb = box_lb(c);
+      if (lb < best) { best = lb; bc = c; }
+    }
+    // the warp's first active lane decides (queries of a warp are spatial neighbours)
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    c0 = __shfl_sync(0xffffffffu, bc, act ? __ffs(act) - 1 : 0);
   }
 
-  if (active) {
-    int32_t* oi = ids + ((long long)b * N + y) * K;
-    float* od = dists + ((long long)b * N + y) * K;
-    int id[KC];
+  // walk outward: c0, c0+1, c0-1, c0+2, ...
+  const int reach = max(c0, nchunks - 1 - c0);
+  for (int step = 0; step <= 2 * reach; ++step) {
+    const int c = (step & 1) ? c0 + ((step + 1) >> 1) : c0 - (step >> 1);
+    if (c < 0 || c >= nchunks) continue;
+    if (!__any_sync(0xffffffffu, box_lb(c) <= thr2)) continue;
+    const float4* cand = cloud + c * kKnnChunk;
+    for (int j0 = 0; j0 < kKnnChunk; j0 += 8) {
 #pragma unroll
-    for (int j = 0; j < KC; ++j) id[j] = (rk[j] == INT_MAX) ? -1 : knn_point_of(rk[j], T, logV);
+      for (int u = 0; u < 8; ++u) {
+        const float4 v = __ldg(cand + j0 + u);
+        const float d2 = M::d2(v.x - qx, v.y - qy, v.z - qz);
+        if (d2 <= thr2) {
+          s_buf[cnt][tid] = make_float2(d2, v.w);
+          ++cnt;
+        }
+      }
+      if (__any_sync(0xffffffffu, cnt > kKnnCap - 8)) flush();
+    }
+    if (__any_sync(0xffffffffu, cnt >= flush_min)) flush();
+  }
+  flush();
+
+  if (active) {
+    int32_t* oi = ids + ((long long)b * Nq + y) * K;
+    float* od = dists + ((long long)b * Nq + y) * K;
+    int id[KC];
+    float ky[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      const int r = (int)(uint32_t)(L[j] & 0xffffffffull);
+      ky[j] = __uint_as_float((uint32_t)(L[j] >> 32));
+      id[j] = (SELF && r == INT_MAX) ? -1 : M::point_of(r, T, logV);
+    }
     if constexpr (EXACT && KC % 4 == 0) {
 #pragma unroll
       for (int j = 0; j < KC; j += 4) {
         *reinterpret_cast<int4*>(oi + j) = make_int4(id[j], id[j + 1], id[j + 2], id[j + 3]);
-        *reinterpret_cast<float4*>(od + j) = make_float4(sq[j], sq[j + 1], sq[j + 2], sq[j + 3]);
+        *reinterpret_cast<float4*>(od + j) = make_float4(ky[j], ky[j + 1], ky[j + 2], ky[j + 3]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < KC; ++j)
-        if (j < K) { oi[j] = id[j]; od[j] = sq[j]; }
+        if (j < K) { oi[j] = id[j]; od[j] = ky[j]; }
     }
   }
+}
+
+static int knn_flush_min() {
+  static const int v = [] {
+    const char* e = getenv("DH3D_KNN_FLUSH");
+    const int x = e ? atoi(e) : 1;
+    return x < 1 ? 1 : x;
+  }();
+  return v;
 }
 
 int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
@@ -340,9 +433,11 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(Np, kKnnThreads), B);
   const bool vec_ok = (((uintptr_t)ids | (uintptr_t)dists) & 15) == 0;
-#define DH3D_KNN(KC, EX)                                                                        \
-  knn_query_kernel<KC, EX><<<grid, kKnnThreads, 0, st>>>(sorted, boxes, N, Np, o.T, o.logT, o.logV, K, \
-                                                         ids, dists)
+  const int fm = knn_flush_min();
+#define DH3D_KNN(KC, EX)                                                                              \
+  knn_query_kernel<KC, EX, true, KnnMetric><<<grid, kKnnThreads, 0, st>>>(sorted, N, Np, sorted, boxes, Np, \
+                                                                          o.T, o.logT, o.logV, K, fm, ids,   \
+                                                                          dists)
   if (K == 8 && vec_ok) DH3D_KNN(8, true);
   else if (K == 16 && vec_ok) DH3D_KNN(16, true);
   else if (K == 32 && vec_ok) DH3D_KNN(32, true);
@@ -351,6 +446,42 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   else if (K <= 16) DH3D_KNN(16, false);
   else DH3D_KNN(32, false);
 #undef DH3D_KNN
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------
+// three_nn through the same engine: Morton-sort the known points (candidates + chunk boxes) and the
+// query points (spatially coherent warps), scan with the reference's un-fused arithmetic.
+// workspace: B * { float4[np2] candidates, float4[2*np2/64] their boxes, float4[np1] queries,
+//                   float4[2*np1/64] query-chunk boxes (written by the sort, unused) }
+// ---------------------------------------------------------------------------------------------
+size_t three_nn_workspace_bytes(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 0;
+  const size_t np1 = knn_padded(n), np2 = knn_padded(m);
+  return (size_t)b * (np2 + 2 * (np2 / kKnnChunk) + np1 + 2 * (np1 / kKnnChunk)) * sizeof(float4);
+}
+
+int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                           int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!xyz1 || !xyz2 || !dist || !idx) return DH3D_ERR_NULL;
+  if (b <= 0 || n <= 0 || m <= 0) return DH3D_ERR_DIM;
+  if (b > 65535) return DH3D_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < three_nn_workspace_bytes(b, n, m)) return DH3D_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 127) != 0) return DH3D_ERR_ALIGN;
+  const int np1 = knn_padded(n), np2 = knn_padded(m);
+  float4* cands = reinterpret_cast<float4*>(workspace);
+  float4* boxes = cands + (size_t)b * np2;
+  float4* queries = boxes + (size_t)b * 2 * (np2 / kKnnChunk);
+  float4* qboxes = queries + (size_t)b * np1;
+  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, queries, qboxes);
+  int rc = launch_status();
+  if (rc != DH3D_OK) return rc;
+  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, cands, boxes);
+  rc = launch_status();
+  if (rc != DH3D_OK) return rc;
+  dim3 grid(ceil_div(np1, kKnnThreads), b);
+  knn_query_kernel<4, false, false, ThreeNnMetric><<<grid, kKnnThreads, 0, st>>>(
+      queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, knn_flush_min(), idx, dist);
   return launch_status();
 }
 

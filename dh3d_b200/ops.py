@@ -120,13 +120,20 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
-def three_nn(xyz1, xyz2):
+def three_nn(xyz1, xyz2, exhaustive=False):
+    """3 nearest xyz2 points of every xyz1 point (squared distances, reference arithmetic and ties).
+    Default: Morton-sorted box-pruned scan (same results); exhaustive=True: the plain tiled scan."""
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     dist = torch.empty((B, n, 3), dtype=f32, device=xyz1.device)
     idx = torch.empty((B, n, 3), dtype=i32, device=xyz1.device)
-    call("dh3d_three_nn", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
-         check(dist, f32, "dist"), check(idx, i32, "idx"), stream_ptr(xyz1.device))
+    if exhaustive:
+        call("dh3d_three_nn", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
+             check(dist, f32, "dist"), check(idx, i32, "idx"), stream_ptr(xyz1.device))
+        return dist, idx
+    ws, wp, wn = workspace(query("dh3d_three_nn_workspace_bytes", B, n, m), xyz1.device)
+    call("dh3d_three_nn_ws", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
+         check(dist, f32, "dist"), check(idx, i32, "idx"), wp, wn, stream_ptr(xyz1.device))
     return dist, idx
 
 

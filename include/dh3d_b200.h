@@ -142,6 +142,11 @@ DH3D_API int dh3d_query_ball_point(int b, int n, int m, float radius, int nsampl
                           size_t workspace_bytes, void* stream);
 DH3D_API int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
                   int32_t* idx, void* stream);
+/* Same results through the k-NN engine (Morton-sorted known points with chunk bounding boxes, exact
+ * box skipping with the reference's un-fused arithmetic): needs a caller workspace. */
+DH3D_API size_t dh3d_three_nn_workspace_bytes(int b, int n, int m);
+DH3D_API int dh3d_three_nn_ws(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                     int32_t* idx, void* workspace, size_t workspace_bytes, void* stream);
 DH3D_API int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
                            const float* weight, float* out, void* stream);
 /* fused caller-side step of core/backbones.py:91-96: weight = (1/max(d,1e-10))/sum(...) computed

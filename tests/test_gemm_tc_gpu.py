@@ -1,4 +1,5 @@
-"""GPU tests of the tcgen05 (3xTF32) GEMM path against fp64 and against the exact-fp32 FFMA path."""
+"""GPU tests of the tcgen05 GEMM path (default: fp16-pair split on kind::f16, gemm_tc16.cu; DH3D_GEMM_SPLIT=tf32:
+3xTF32, gemm_tc.cu) against fp64 and against the exact-fp32 FFMA path."""
 import numpy as np
 import pytest
 import torch
@@ -69,3 +70,35 @@ def test_linear_rowdot_fused_head(M, K, N):
     else:
         e = ops.rowdot(ops.linear(dx, dw, scale=dsc, shift=dsh, act=1), dw2, bias=0.125, act=2).cpu().numpy()
     assert np.abs(y.cpu().numpy() - e).max() < 5e-5
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("xmag,wmag", [(1e-3, 1.0), (100.0, 1.0), (1.0, 1e-6), (1.0, 1e4), (0.02, 300.0)])
+def test_linear_packed_dynamic_range(xmag, wmag):
+    """The fp16-pair split scales activations by 2^4 and every weight column by its own power of two:
+    accuracy must hold for small / large activations and any weight magnitude."""
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(5)
+    x = (rng.randn(2048, 256) * xmag).astype(np.float32)
+    w = (rng.randn(256, 256) / 16 * wmag).astype(np.float32)
+    w[:, 7] *= 1e-4   # one tiny and one huge column
+    w[:, 9] *= 1e3
+    dx, dw = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    y = ops.linear(dx, dw, packed=ops.linear_prepack(dw)).cpu().numpy()
+    e = x.astype(np.float64) @ w.astype(np.float64)
+    err = np.abs(y - e).max(axis=0) / np.sqrt((e ** 2).mean(axis=0))   # per output column
+    assert err.max() < 6e-5, (err.max(), int(err.argmax()))
+
+
+@pytest.mark.timeout(600)
+def test_tf32_split_path_in_subprocess():
+    """DH3D_GEMM_SPLIT is read once per process: run this file's accuracy tests on the 3xTF32 kernels."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DH3D_GEMM_SPLIT") == "tf32":
+        pytest.skip("already the tf32 run")
+    env = dict(os.environ, DH3D_GEMM_SPLIT="tf32")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
+                        "vs_fp64 or rowdot or strided"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

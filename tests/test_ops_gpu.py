@@ -169,6 +169,14 @@ def test_conv_pointset_reference_fixture_and_dh3d_shape():
     sc, sh = rng.rand(32).astype(np.float32) + 0.5, rng.randn(32).astype(np.float32)
     out = ops.conv_pointset(cu(pts), cu(th), cu(bi), cu(nb), scale=cu(sc), shift=cu(sh), act=1)
     close(out, np.maximum(exp.transpose(0, 2, 1) * sc + sh, 0))
+    # ragged row count (tail of the 8-lanes-per-point fast path) and the generic kernel (Dout != 32)
+    pts = make_cloud(rng, 3, 1001)
+    nb, _ = oracle.knn_bruteforce(np.ascontiguousarray(pts.transpose(0, 2, 1)), 8)
+    for dout in (32, 40):
+        th, bi = rng.randn(3, dout).astype(np.float32), rng.randn(dout).astype(np.float32)
+        exp = oracle.convolution_pointset(pts.transpose(0, 2, 1), nb.transpose(0, 2, 1), th, bi)
+        out = ops.conv_pointset(cu(pts), cu(th), cu(bi), cu(nb))
+        assert np.array_equal(out.cpu().numpy().transpose(0, 2, 1), exp)
 
 
 # ---------------------------------------------------------------------------------------- FlexConv
@@ -253,10 +261,11 @@ def test_three_nn_bitexact(B, n, m):
         b[:, 50:60] = b[:, 40:50]  # duplicated known points -> strict '<' keeps the earlier index
         h = min(n, m) // 2
         a[:, :h] = b[:, :h]  # exact hits -> dist 0
-    dist, idx = tf_ops.three_nn(cu(a), cu(b))
+    from dh3d_b200 import ops
     ed, ei = oracle.three_nn(a, b)
-    assert np.array_equal(idx.cpu().numpy(), ei)
-    assert np.array_equal(dist.cpu().numpy(), ed)
+    for dist, idx in (tf_ops.three_nn(cu(a), cu(b)), ops.three_nn(cu(a), cu(b), exhaustive=True)):
+        assert np.array_equal(idx.cpu().numpy(), ei)
+        assert np.array_equal(dist.cpu().numpy(), ed)
 
 
 def test_three_interpolate_bitexact_and_fused_weights():

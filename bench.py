@@ -120,7 +120,42 @@ def algorithmic(tag, name):
     if name == "dh3d_knn_bruteforce_pm":
         B, N, K = d["B"], d["N"], d["K"]
         return B * (12.0 * N + 8.0 * N * K), 8.0 * B * N * N
+    if name == "dh3d_netvlad":   # 4*[nD + n + 2*D*Kc + 256] per cloud + the hidden weights once
+        B, N, D, Kc, O = d["B"], d["N"], d["D"], d["Kc"], d["O"]
+        return 4.0 * (B * (N * D + N + O) + 2 * D * Kc + D * Kc * O), B * 4.0 * N * D * Kc
+    if name == "dh3d_farthest_point_sample":
+        B, N, M = d["B"], d["N"], d["M"]
+        return B * (12.0 * N + 4.0 * M), 8.0 * B * N * (M - 1)
     return 0.0, 0.0
+
+
+# C-ABI entry point -> the kernel that dominates it (prefix of the ncu kernel name), for roofline.traffic
+OP_KERNEL = {
+    "dh3d_linear_rowdot_packed": ("gemm_tc16_kernel", "gemm_tc_kernel"),
+    "dh3d_linear_packed": ("gemm_tc16_kernel", "gemm_tc_kernel"),
+    "dh3d_netvlad": ("netvlad_aggregate_kernel",),
+    "dh3d_knn_bruteforce_pm": ("knn_query_kernel<8, 1, 1",),
+    "dh3d_farthest_point_sample": ("fps_reg_kernel",),
+    "dh3d_flex_conv_pm": ("flexconv_tc_kernel",),
+}
+
+
+def ncu_traffic(op_name, avg_launch_us):
+    """dram read+write bytes per launch of the op's dominant kernel from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, made by scripts/ncu_summary.py traffic); the capture whose
+    duration is closest to the live launch time is the same shape.  None if there is no capture."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path) or op_name not in OP_KERNEL:
+        return None
+    with open(path) as f:
+        caps = json.load(f)
+    cand = [c for c in caps if c["kernel"].startswith(OP_KERNEL[op_name])]
+    if not cand:
+        return None
+    best = min(cand, key=lambda c: abs(c["time_us"] - avg_launch_us))
+    if abs(best["time_us"] - avg_launch_us) > 0.5 * avg_launch_us:
+        return None
+    return best["dram_bytes"]
 
 
 def use_all_host_threads():
@@ -375,23 +410,34 @@ def main():
     tag = dominant.split("[")[1].rstrip("]") if "[" in dominant else ""
     abytes, aflops = algorithmic(tag, dom_name) if tag else (0.0, 0.0)
     avg_s = (tot_ms / max(calls, 1)) / 1e3
+    traffic = ncu_traffic(dom_name, avg_s * 1e6)
     if dom_name.startswith("dh3d_linear"):
         ach = aflops / avg_s / 1e12
-        tc = dom_name != "dh3d_linear"
+        f16 = os.environ.get("DH3D_GEMM_SPLIT", "f16")[:1].lower() != "t"
+        if dom_name == "dh3d_linear":
+            how = "fp32 FFMA kernel (DH3D_GEMM=simt)."
+        elif f16:
+            how = ("The kernel executes 3 fp16 tcgen05 MMAs per product (2-term fp16 split, kind::f16, same rate "
+                   "as bf16), so it issues %.0f TFLOP/s of tensor work = %.2f of the measured bf16 peak."
+                   % (3 * ach, 3 * ach / peaks["bf16_tflops_sustained"]))
+        else:
+            how = ("The kernel executes 3 TF32 tcgen05 MMAs per product (3xTF32 split) and TF32 runs at half the "
+                   "bf16 rate, so it issues %.0f TFLOP/s of TF32 work = %.2f of the TF32 pipe (measured bf16 "
+                   "peak / 2)." % (3 * ach, 3 * ach / (peaks["bf16_tflops_sustained"] / 2)))
         roof = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic,
                 "kernel": dominant, "avg_launch_ms": avg_s * 1e3, "launches_timed": calls,
                 "peak_source": peaks["source"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",
-                "note": "achieved = algorithmic 2*M*K*N flops of an fp32-accurate GEMM. " +
-                        ("The kernel executes 3 TF32 tcgen05 MMAs per product (3xTF32 split) and TF32 runs at "
-                         "half the bf16 rate, so it issues %.0f TFLOP/s of TF32 work = %.2f of the TF32 pipe "
-                         "(measured bf16 peak / 2)." % (3 * ach, 3 * ach / (peaks["bf16_tflops_sustained"] / 2))
-                         if tc else "fp32 FFMA kernel (DH3D_GEMM=simt).")}
+                "algorithmic_bytes": abytes,
+                "note": "achieved = algorithmic 2*M*K*N flops of an fp32-accurate GEMM. " + how}
     else:
         ach = abytes / avg_s / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / peaks["hbm_gbs"], "traffic": None, "kernel": dominant,
-                "avg_launch_ms": avg_s * 1e3, "launches_timed": calls, "peak_source": peaks["source"]}
+                "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "kernel": dominant,
+                "avg_launch_ms": avg_s * 1e3, "launches_timed": calls, "peak_source": peaks["source"],
+                "algorithmic_bytes": abytes, "algorithmic_flops": aflops}
+    if traffic is not None:
+        roof["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read+write per launch)"
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------
     cpu = None

@@ -85,8 +85,10 @@ def conv_pointset(features, theta, bias, neighborhood, scale=None, shift=None, a
 def farthest_point_sample(npoint, inp):
     B, N, _ = inp.shape
     out = torch.empty((B, npoint), dtype=i32, device=inp.device)
+    _lib.stats.tag = "B%d_N%d_M%d" % (B, N, int(npoint))
     call("dh3d_farthest_point_sample", B, N, int(npoint), check(inp, f32, "inp", 3),
          check(out, i32, "out"), stream_ptr(inp.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -282,6 +284,7 @@ def netvlad(features, att, cluster_weights, cluster_bn, cluster_weights2, hidden
     if nbytes == 0:
         raise _lib.Dh3dError("netvlad: unsupported configuration D=%d Kc=%d out=%d" % (D, Kc, out_dim))
     ws, wp, wn = workspace(nbytes, features.device)
+    _lib.stats.tag = "B%d_N%d_D%d_Kc%d_O%d" % (B, N, D, Kc, out_dim)
     call("dh3d_netvlad", check(features, f32, "features", 3), check(att, f32, "att"), B, N, D, Kc,
          out_dim, check(cluster_weights, f32, "cluster_weights"), check(cluster_bn[0], f32, "cbn_s"),
          check(cluster_bn[1], f32, "cbn_b"), check(cluster_weights2.reshape(D, Kc), f32, "cw2"),
@@ -289,4 +292,5 @@ def netvlad(features, att, cluster_weights, cluster_bn, cluster_weights2, hidden
          check(bn[1], f32, "bn_b"), check(gating_weights, f32, "gating_weights"),
          check(gating_bn[0], f32, "gbn_s"), check(gating_bn[1], f32, "gbn_b"), int(bool(final_l2norm)),
          check(out, f32, "out"), wp, wn, stream_ptr(features.device))
+    _lib.stats.tag = None
     return out

@@ -25,16 +25,26 @@ int flexconv_fused_launch(const float* feat, const float* xyz, const int32_t* nb
                           const float* scale, const float* shift, int act, float* out, int rows,
                           int n_per_cloud, int K, int Din, int Dout, cudaStream_t st);
 bool flexconv_fused_supported(int Din, int Dout);
+int flexconv_g4_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
+                       const float* scale, const float* shift, int act, float* out, int rows, int n_per_cloud,
+                       int K, int Din, int Dout, cudaStream_t st);
 
-// DH3D_FLEXCONV=split keeps the two-kernel form (moments to HBM, then the GEMM); default is the fused
-// gather -> moments -> tcgen05 kernel of flexconv_tc.cu whenever the tensor-core path is on.
-static bool flexconv_use_fused() {
-  static const bool f = [] {
+// Fused kernels (tensor-core path on): default = cp.async-staged neighbours (flexconv_ca.cu);
+// DH3D_FLEXCONV=g4: TMA tile::gather4 staging (flexconv_g4.cu); =regs: per-thread loads (flexconv_tc.cu);
+// =split: the two-kernel form (moments to HBM, then the GEMM).
+static int flexconv_mode() {   // 0 = ca, 1 = regs, 2 = split, 3 = g4
+  static const int m = [] {
     const char* e = getenv("DH3D_FLEXCONV");
-    return !(e && (e[0] == 's' || e[0] == 'S'));
+    if (e && (e[0] == 's' || e[0] == 'S')) return 2;
+    if (e && (e[0] == 'r' || e[0] == 'R')) return 1;
+    if (e && (e[0] == 'g' || e[0] == 'G')) return 3;
+    return 0;
   }();
-  return f;
+  return m;
 }
+int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
+                       const float* scale, const float* shift, int act, float* out, int rows, int n_per_cloud,
+                       int K, int Din, int Dout, cudaStream_t st);
 int transpose_launch(const void* src, void* dst, int B, int R, int C, cudaStream_t st);
 int transpose_strided_launch(const void* src, long long sbs, int lds, void* dst, long long sbd,
                              int ldd, int B, int R, int C, cudaStream_t st);
@@ -180,9 +190,18 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
 
   const long long rows = (long long)B * N;
   if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
-  if (tc && flexconv_use_fused() && flexconv_fused_supported(Din, Dout))
+  if (tc && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) {
+    // measured (B200, r1h): cp.async staging wins for Din >= 64 (0.2125 vs 0.2216 ms at 64->64 x 262144 points,
+    // 0.111 vs 0.130 ms at 128->256 x 32768), the per-thread gather for Din = 32 (0.122 vs 0.139 ms)
+    if (flexconv_mode() == 0 && Din >= 64)
+      return flexconv_ca_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
+                                Dout, st);
+    if (flexconv_mode() == 3)
+      return flexconv_g4_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
+                                Dout, st);
     return flexconv_fused_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
                                  Dout, st);
+  }
   long long blocks = (rows * (Din / 4) + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   flexconv_moments_kernel<<<(int)blocks, 256, 0, st>>>(feat, xyz, nbr, A, rows, N, K, Din);

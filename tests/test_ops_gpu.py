@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star): bit-exact for k-NN / FPS / grouping / ball-quer
 for pure-select float outputs; FlexConv / ConvPointset / interpolation / NetVLAD within 1e-4
 relative fp32 (stated per test as rtol with an atol tied to the output scale).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -205,7 +207,8 @@ def test_flex_conv_reference_fixture_odd_dims():
 
 @pytest.mark.parametrize("B,N,K,Din,Dout", [(2, 1024, 8, 32, 64), (1, 8192, 8, 64, 64), (2, 1024, 8, 64, 128),
                                             (2, 1024, 8, 128, 128), (1, 1024, 8, 128, 256), (1, 2048, 16, 128, 128),
-                                            (1, 512, 32, 128, 128), (1, 300, 5, 8, 12)])
+                                            (1, 512, 32, 128, 128), (1, 300, 5, 8, 12), (3, 333, 8, 32, 64),
+                                            (2, 777, 11, 64, 72)])
 def test_flex_conv_pm_vs_fp64_truth(B, N, K, Din, Dout):
     from dh3d_b200 import ops
     rng = np.random.RandomState(N + Din + Dout + K)
@@ -235,6 +238,22 @@ def test_flex_conv_fused_epilogue_and_cm_entry():
     out_cm = user_ops.flex_convolution(cu(f.transpose(0, 2, 1)), cu(pts.transpose(0, 2, 1)),
                                        cu(nb.transpose(0, 2, 1)), cu(th), cu(bi))
     close(out_cm, exp)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("mode", ["regs", "split", "g4"])
+def test_flex_conv_other_kernels_in_subprocess(mode):
+    """DH3D_FLEXCONV is read once per process: run the FlexConv accuracy tests on the per-thread-gather fused
+    kernel (flexconv_tc.cu), the TMA gather4 kernel (flexconv_g4.cu) and the two-kernel form as well (default =
+    cp.async staging, flexconv_ca.cu)."""
+    import subprocess
+    import sys
+    if os.environ.get("DH3D_FLEXCONV"):
+        pytest.skip("already a non-default FlexConv run")
+    env = dict(os.environ, DH3D_FLEXCONV=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
+                        "flex_conv_pm_vs_fp64_truth or fused_epilogue"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_flex_conv_centre_is_the_point_itself_on_duplicates():

@@ -11,6 +11,8 @@
 // read exactly once per batch), and the head kernel applies BN, context gating and the final
 // l2-normalise.
 //   D == 256 features, Kc == 64 clusters, out_dim == 256 (the shipped DH3D configuration).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dh3d {
@@ -262,10 +264,24 @@ static size_t nv_part_h_bytes(int B) {
   return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
 }
 
+// netvlad_tc.cu: the aggregation on the tensor cores (default); DH3D_NETVLAD=simt keeps the FFMA kernel above
+size_t netvlad_tc_workspace_bytes();
+int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, int N, const float* cw,
+                                const float* bn_scale, const float* bn_shift, float* part_v, float* part_s,
+                                int* P_out, void* ws, cudaStream_t st);
+static bool netvlad_use_tc() {
+  static const bool tc = [] {
+    const char* e = getenv("DH3D_NETVLAD");
+    return !(e && (e[0] == 's' || e[0] == 'S'));
+  }();
+  return tc;
+}
+
 size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
   (void)N;
   if (B <= 0 || D != kVD || Kc != kVK || out_dim != kVD) return 0;
-  return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_part_h_bytes(B);
+  return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_part_h_bytes(B) +
+         align_up(netvlad_tc_workspace_bytes(), 256);
 }
 
 int netvlad_launch(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
@@ -286,7 +302,23 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   float* part_v = reinterpret_cast<float*>(p); p += nv_part_v_bytes(B);
   float* part_s = reinterpret_cast<float*>(p); p += nv_part_s_bytes(B);
   float* vlad = reinterpret_cast<float*>(p); p += nv_vlad_bytes(B);
-  float* part_h = reinterpret_cast<float*>(p);
+  float* part_h = reinterpret_cast<float*>(p); p += nv_part_h_bytes(B);
+  void* tc_ws = p;
+
+  int rc;
+  if (netvlad_use_tc()) {
+    int P = 0;
+    rc = netvlad_tc_aggregate_launch(features, att, B, N, cw, cbn_scale, cbn_shift, part_v, part_s, &P, tc_ws, st);
+    if (rc != DH3D_OK) return rc;
+    netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, P, cw2, vlad);
+    if ((rc = launch_status()) != DH3D_OK) return rc;
+    const int slices = kVD * kVK / kVSlice;
+    netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
+    if ((rc = launch_status()) != DH3D_OK) return rc;
+    netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
+                                          final_l2norm, out);
+    return launch_status();
+  }
 
   cudaError_t e = cudaFuncSetAttribute(netvlad_aggregate_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -299,7 +331,7 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   while (slabs > 1 && (N + slabs - 1) / slabs < 64) --slabs;
   netvlad_aggregate_kernel<<<dim3(slabs, B), kVD, sizeof(VladSmem), st>>>(
       features, att, N, slabs, cw, cbn_scale, cbn_shift, part_v, part_s);
-  int rc = launch_status();
+  rc = launch_status();
   if (rc != DH3D_OK) return rc;
   netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, slabs, cw2, vlad);
   if ((rc = launch_status()) != DH3D_OK) return rc;

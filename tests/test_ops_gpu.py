@@ -374,3 +374,34 @@ def test_netvlad_vs_fp64(B, N):
     close(out, net.netvlad(feat, att, p, final_l2norm=True))
     raw = blk(None, cu(feat), cu(att), final_l2norm=False)
     close(raw, net.netvlad(feat, att, p, final_l2norm=False))
+
+
+@pytest.mark.timeout(300)
+def test_netvlad_simt_kernel_and_degenerate_rows_in_subprocess():
+    """DH3D_NETVLAD is read once per process: the FFMA aggregation kernel (netvlad.cu) must still pass."""
+    import subprocess
+    import sys
+    if os.environ.get("DH3D_NETVLAD"):
+        pytest.skip("already the simt run")
+    env = dict(os.environ, DH3D_NETVLAD="simt")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k", "netvlad_vs_fp64"],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_netvlad_tiny_and_huge_feature_norms():
+    """Rows are l2-normalised before the fp16 split: feature magnitude must not matter (1e-6 .. 1e4), and an
+    all-zero row contributes the reference's zero vector (epsilon 1e-12 on the squared norm)."""
+    from dh3d_b200.backbones import GlobalNetVLADBlock
+    from dh3d_b200.model import init_random_
+    from oracle import net
+    blk = init_random_(GlobalNetVLADBlock(), seed=9)
+    p = {"netvlad." + k: v.detach().numpy() for k, v in blk.named_parameters()}
+    blk = blk.cuda()
+    rng = np.random.RandomState(77)
+    feat = rng.randn(2, 1000, 256).astype(np.float32)
+    feat *= (10.0 ** rng.uniform(-6, 4, (2, 1000, 1))).astype(np.float32)
+    feat[0, 5] = 0
+    att = rng.rand(2, 1000, 1).astype(np.float32)
+    out = blk(None, cu(feat), cu(att), final_l2norm=True)
+    close(out, net.netvlad(feat, att, p, final_l2norm=True))

@@ -57,6 +57,18 @@ _SIGNATURES = {
     "dh3d_topk_l2": (_c_int, [_p, _c_int, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p]),
     "dh3d_netvlad_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "dh3d_netvlad": (_c_int, [_p, _p] + [_c_int] * 5 + [_p] * 10 + [_c_int, _p, _p, _c_size_t, _p]),
+    "dh3d_flex_conv_grad_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "dh3d_flex_conv_grad": (_c_int, [_p] * 9 + [_c_int] * 5 + [_p, _c_size_t, _p]),
+    "dh3d_flex_conv_grad_pm_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "dh3d_flex_conv_grad_pm": (_c_int, [_p] * 9 + [_c_int] * 5 + [_p, _c_size_t, _p]),
+    "dh3d_flex_pool_grad": (_c_int, [_p] * 3 + [_c_int] * 3 + [_p]),
+    "dh3d_conv_pointset_grad_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "dh3d_conv_pointset_grad": (_c_int, [_p] * 7 + [_c_int] * 5 + [_p, _c_size_t, _p]),
+    "dh3d_flex_deconv_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "dh3d_flex_deconv": (_c_int, [_p] * 6 + [_c_int] * 5 + [_p, _c_size_t, _p]),
+    "dh3d_group_point_grad": (_c_int, [_c_int] * 5 + [_p, _p, _p, _p]),
+    "dh3d_gather_point_grad": (_c_int, [_c_int] * 3 + [_p, _p, _p, _p]),
+    "dh3d_three_interpolate_grad": (_c_int, [_c_int] * 4 + [_p] * 5),
 }
 
 _lib = None
@@ -67,6 +79,7 @@ _KERNELS_PER_CALL = {
     "dh3d_flex_conv": 8,                                             # 4 transposes + theta_ext + moments + gemm (+memset)
     "dh3d_flex_conv_pm": 3,                                          # theta_ext + moments + gemm (+1 if feature_bias)
     "dh3d_query_ball_point": 2, "dh3d_netvlad": 4, "dh3d_three_nn_ws": 3,
+    "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
 }
 
 

@@ -73,6 +73,30 @@ int flex_conv_pm(const float* feat, const float* theta, const float* bias, const
 int flex_conv_cm(const float* feat_cm, const float* theta, const float* bias, const int32_t* nbr_cm,
                  const float* pos_cm, float* out_cm, int B, int N, int K, int Din, int Dout, void* ws,
                  size_t ws_bytes, cudaStream_t st);
+// backward.cu
+size_t flex_conv_grad_pm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int flex_conv_grad_pm(const float* feat, const float* theta, const float* bias, const int32_t* nbr, const float* xyz,
+                      const float* topdiff, float* grad_feat, float* grad_theta, float* grad_bias, int B, int N, int K,
+                      int Din, int Dout, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t flex_conv_grad_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int flex_conv_grad_cm(const float* feat_cm, const float* theta, const float* bias, const int32_t* nbr_cm,
+                      const float* pos_cm, const float* topdiff_cm, float* grad_feat_cm, float* grad_theta,
+                      float* grad_bias, int B, int N, int K, int Din, int Dout, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
+size_t flex_deconv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int flex_deconv_cm(const float* feat_cm, const float* theta, const float* bias, const int32_t* nbr_cm,
+                   const float* pos_cm, float* out_cm, int B, int N, int K, int Din, int Dout, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int flex_pool_grad_cm(const float* topdiff, const int32_t* argmax, float* grad_feat, int B, int N, int D,
+                      cudaStream_t st);
+size_t conv_pointset_grad_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int conv_pointset_grad_cm(const float* feat_cm, const float* theta, const int32_t* nbr_cm, const float* topdiff_cm,
+                          float* grad_feat_cm, float* grad_theta, float* grad_bias, int B, int N, int K, int Din,
+                          int Dout, void* ws, size_t ws_bytes, cudaStream_t st);
+int group_point_grad_launch(int b, int n, int c, int m, int nsample, const float* grad_out, const int32_t* idx,
+                            float* grad_points, cudaStream_t st);
+int three_interpolate_grad_launch(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
+                                  const float* weight, float* grad_points, cudaStream_t st);
 // topk.cu
 int topk_l2_launch(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                    int32_t* idx, float* val, cudaStream_t st);
@@ -296,6 +320,62 @@ int dh3d_netvlad(const float* features, const float* att, int B, int N, int D, i
                         cluster_bn_shift, cluster_weights2, hidden1_weights, bn_scale, bn_shift,
                         gating_weights, gating_bn_scale, gating_bn_shift, final_l2norm, out,
                         workspace, workspace_bytes, S(stream));
+}
+
+size_t dh3d_flex_conv_grad_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_conv_grad_cm_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_conv_grad(const float* features_cm, const float* theta, const float* bias,
+                        const int32_t* neighborhood_cm, const float* positions_cm, const float* topdiff_cm,
+                        float* grad_features_cm, float* grad_theta, float* grad_bias, int B, int N, int K,
+                        int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream) {
+  return flex_conv_grad_cm(features_cm, theta, bias, neighborhood_cm, positions_cm, topdiff_cm, grad_features_cm,
+                           grad_theta, grad_bias, B, N, K, Din, Dout, workspace, workspace_bytes, S(stream));
+}
+size_t dh3d_flex_conv_grad_pm_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_conv_grad_pm_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_conv_grad_pm(const float* features_pm, const float* theta, const float* bias,
+                           const int32_t* neighborhood_pm, const float* xyz_pm, const float* topdiff_pm,
+                           float* grad_features_pm, float* grad_theta, float* grad_bias, int B, int N, int K,
+                           int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream) {
+  return flex_conv_grad_pm(features_pm, theta, bias, neighborhood_pm, xyz_pm, topdiff_pm, grad_features_pm, grad_theta,
+                           grad_bias, B, N, K, Din, Dout, workspace, workspace_bytes, S(stream));
+}
+int dh3d_flex_pool_grad(const float* topdiff_cm, const int32_t* argmax_cm, float* grad_features_cm, int B, int N,
+                        int D, void* stream) {
+  return flex_pool_grad_cm(topdiff_cm, argmax_cm, grad_features_cm, B, N, D, S(stream));
+}
+size_t dh3d_conv_pointset_grad_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return conv_pointset_grad_cm_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_conv_pointset_grad(const float* features_cm, const float* theta, const int32_t* neighborhood_cm,
+                            const float* topdiff_cm, float* grad_features_cm, float* grad_theta,
+                            float* grad_bias, int B, int N, int K, int Din, int Dout, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return conv_pointset_grad_cm(features_cm, theta, neighborhood_cm, topdiff_cm, grad_features_cm, grad_theta, grad_bias,
+                               B, N, K, Din, Dout, workspace, workspace_bytes, S(stream));
+}
+size_t dh3d_flex_deconv_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_deconv_cm_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_deconv(const float* features_cm, const float* theta, const float* bias,
+                     const int32_t* neighborhood_cm, const float* positions_cm, float* out_cm, int B, int N,
+                     int K, int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream) {
+  return flex_deconv_cm(features_cm, theta, bias, neighborhood_cm, positions_cm, out_cm, B, N, K, Din, Dout, workspace,
+                        workspace_bytes, S(stream));
+}
+int dh3d_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int32_t* idx,
+                          float* grad_points, void* stream) {
+  return group_point_grad_launch(b, n, c, m, nsample, grad_out, idx, grad_points, S(stream));
+}
+int dh3d_gather_point_grad(int b, int n, int m, const float* out_g, const int32_t* idx, float* inp_g,
+                           void* stream) {
+  return group_point_grad_launch(b, n, 3, m, 1, out_g, idx, inp_g, S(stream));
+}
+int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
+                                const float* weight, float* grad_points, void* stream) {
+  return three_interpolate_grad_launch(b, n, c, m, grad_out, idx, weight, grad_points, S(stream));
 }
 
 }  // extern "C"

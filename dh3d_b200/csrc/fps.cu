@@ -13,6 +13,8 @@
 // [t*PPT, (t+1)*PPT), scan them in increasing tk with a strict `>`, and break cross-thread ties
 // towards the lowest thread -- the same total order.  d = fma(dz,dz,fma(dx,dx,dy*dy)) is the
 // contraction nvcc applies to :142; d2 = fminf(d, temp).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dh3d {
@@ -90,6 +92,124 @@ fps_reg_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restr
   }
 }
 
+// ---- 4-CTA cluster variant (default for n <= 8192) ----------------------------------------------
+// The single-CTA kernel above is ISSUE-bound, not latency-bound: 32 warps x ~105 instructions per
+// round on one SM's four schedulers = ~840 of the ~1375 cycles a round takes (ncu r1h), while 116
+// of the 148 SMs idle at B = 32.  Here a cluster of 4 CTAs x 256 threads owns one cloud: the same
+// 32 warps, two per scheduler over four SMs.  There is NO barrier inside the round loop: lane r of
+// every warp stores the warp's (d2 bits | round tag | tie rank) as one 8-byte word into slot
+// [round parity][global warp] of CTA r's shared memory (st.shared::cluster -- distributed shared
+// memory), and every warp spins on its own CTA's 32 slots until all carry this round's tag, then
+// reduces them with one REDUX.MAX + ballot.  A slot of parity p is rewritten two rounds later,
+// which its writer can only reach after receiving every warp's next-round word, i.e. after every
+// reader is done with it.  Same selection order as above (global thread g = rank*256 + tid owns
+// tie ranks [g*PPT, (g+1)*PPT); lower slot = lower threads wins ties).
+constexpr int kFpsClusterCtas = 4;
+constexpr int kFpsClusterThreads = 256;
+constexpr int kFpsClusterWarps = kFpsClusterThreads / 32;           // per CTA
+constexpr int kFpsClusterSlots = kFpsClusterCtas * kFpsClusterWarps;  // 32 = one per lane
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_b64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_poll_b64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsClusterThreads, 1)
+fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restrict__ idxs) {
+  extern __shared__ __align__(16) float s_xyz[];  // n*3 floats (each CTA keeps the whole cloud)
+  __shared__ __align__(8) unsigned long long s_slot[2][kFpsClusterSlots];
+
+  const uint32_t rank = cluster_ctarank();
+  const int b = blockIdx.x / kFpsClusterCtas;
+  const float* ds = dataset + (long long)b * n * 3;
+  int32_t* out = idxs + (long long)b * m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = (int)rank * kFpsClusterThreads + tid;  // thread id within the cloud
+
+  for (int j = tid; j < n * 3; j += kFpsClusterThreads) s_xyz[j] = ds[j];
+  if (tid < 2 * kFpsClusterSlots) (&s_slot[0][0])[tid] = 0ull;  // tag 0 = no round
+  __syncthreads();
+  cluster_sync_all();  // every CTA's slots are initialised before any remote store lands
+
+  const int V = (n + 511) >> 9;
+  const unsigned magic = 0xffffffffu / (unsigned)V + 1u;
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int tk = g * PPT + i;
+    const int k = (tk % V) * 512 + tk / V;
+    const bool valid = (tk < 512 * V) && (k < n);
+    px[i] = valid ? s_xyz[k * 3 + 0] : 0.f;
+    py[i] = valid ? s_xyz[k * 3 + 1] : 0.f;
+    pz[i] = valid ? s_xyz[k * 3 + 2] : 0.f;
+    td[i] = valid ? 1e38f : -1.f;
+  }
+
+  // lane r < 4 sends to CTA r; slot index = global warp id
+  const uint32_t slot0 = smem_u32(&s_slot[0][0]);
+  const uint32_t my_slot_off = (uint32_t)((int)rank * kFpsClusterWarps + warp) * 8u;
+  const uint32_t remote0 = mapa_shared(slot0 + my_slot_off, (uint32_t)(lane & (kFpsClusterCtas - 1)));
+  const uint32_t poll0 = slot0 + (uint32_t)lane * 8u;
+
+  int old = 0;
+  if (g == 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+    float best = -1.f;
+    int bslot = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
+      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+      const float d2 = fminf(d, td[i]);
+      td[i] = d2;
+      if (d2 > best) { best = d2; bslot = i; }
+    }
+    const int bits = __float_as_int(best);
+    const int wmax = __reduce_max_sync(0xffffffffu, bits);
+    const unsigned mk = __ballot_sync(0xffffffffu, bits == wmax);
+    const int wi = __shfl_sync(0xffffffffu, g * PPT + bslot, __ffs(mk) - 1);
+    const uint32_t tag = (uint32_t)j & 0xffffu;
+    const uint32_t par = ((uint32_t)j & 1u) * (kFpsClusterSlots * 8u);
+    if (lane < kFpsClusterCtas)
+      st_cluster_b64(remote0 + par,
+                     ((unsigned long long)(uint32_t)wmax << 32) | (tag << 16) | (uint32_t)wi);
+    unsigned long long v;
+    int spins = 0;
+    do {
+      v = ld_poll_b64(poll0 + par);
+      if (++spins > (1 << 24)) __trap();  // a lost peer becomes an error, never a hang
+    } while (!__all_sync(0xffffffffu, (((uint32_t)v >> 16) & 0xffffu) == tag));
+    const int hv = (int)(uint32_t)(v >> 32);
+    const int bmax = __reduce_max_sync(0xffffffffu, hv);
+    const unsigned m2 = __ballot_sync(0xffffffffu, hv == bmax);
+    const unsigned tk = (unsigned)__shfl_sync(0xffffffffu, (int)((uint32_t)v & 0xffffu), __ffs(m2) - 1);
+    const unsigned q = (V == 1) ? tk : __umulhi(tk, magic);
+    old = (int)((tk - q * (unsigned)V) * 512u + q);
+    if (g == 0) out[j] = old;
+  }
+  cluster_sync_all();  // no CTA leaves while a peer could still store into its shared memory
+}
+
 // Large-n variant (n > 8192): running min-distance in shared memory, xyz through L1/L2.
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_smem_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restrict__ idxs) {
@@ -142,6 +262,38 @@ static int fps_launch_reg(int b, int n, int m, const float* inp, int32_t* out, c
   return launch_status();
 }
 
+template <int PPT>
+static int fps_launch_cluster(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
+  size_t smem = (size_t)n * 3 * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(b * kFpsClusterCtas));
+  cfg.blockDim = dim3(kFpsClusterThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kFpsClusterCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT>, n, m, inp, out);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  return launch_status();
+}
+
+// DH3D_FPS=cta selects the single-CTA kernel (read once).
+static bool fps_use_cluster() {
+  static const bool v = [] {
+    const char* e = getenv("DH3D_FPS");
+    return !(e && (e[0] == 'c' || e[0] == 'C') && (e[1] == 't' || e[1] == 'T'));
+  }();
+  return v;
+}
+
 int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
   if (!inp || !out) return DH3D_ERR_NULL;
   if (b <= 0 || n <= 0 || m < 0) return DH3D_ERR_DIM;
@@ -149,6 +301,12 @@ int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t
   if (n > 65536) return DH3D_ERR_UNSUPPORTED;
   const int total = 512 * ((n + 511) / 512);
   const int ppt = ceil_div(total, kFpsThreads);
+  if (ppt <= 8 && fps_use_cluster()) {  // 4 x 256 threads per cloud: same points-per-thread split
+    if (ppt <= 1) return fps_launch_cluster<1>(b, n, m, inp, out, st);
+    if (ppt <= 2) return fps_launch_cluster<2>(b, n, m, inp, out, st);
+    if (ppt <= 4) return fps_launch_cluster<4>(b, n, m, inp, out, st);
+    return fps_launch_cluster<8>(b, n, m, inp, out, st);
+  }
   if (ppt <= 1) return fps_launch_reg<1>(b, n, m, inp, out, st);
   if (ppt <= 2) return fps_launch_reg<2>(b, n, m, inp, out, st);
   if (ppt <= 4) return fps_launch_reg<4>(b, n, m, inp, out, st);

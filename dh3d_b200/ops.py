@@ -110,6 +110,37 @@ def group_point(points, idx):
     return out
 
 
+def group_point_grad(points, idx, grad_out):
+    """tf_grouping.py:57-61 (_group_point_grad): grad_out [B,M,S,C], idx [B,M,S] -> grad_points [B,N,C]."""
+    B, N, C = points.shape
+    _, M, S = idx.shape
+    gp = torch.empty((B, N, C), dtype=f32, device=grad_out.device)
+    call("dh3d_group_point_grad", B, N, C, M, S, check(grad_out, f32, "grad_out", 4), check(idx, i32, "idx", 3),
+         check(gp, f32, "grad_points"), stream_ptr(grad_out.device))
+    return gp
+
+
+def gather_point_grad(inp, idx, out_g):
+    """tf_sampling.py:47-51 (_gather_point_grad): out_g [B,M,3], idx [B,M] -> inp_g [B,N,3]."""
+    B, N, _ = inp.shape
+    M = idx.shape[1]
+    gp = torch.empty((B, N, 3), dtype=f32, device=out_g.device)
+    call("dh3d_gather_point_grad", B, N, M, check(out_g, f32, "out_g", 3), check(idx, i32, "idx", 2),
+         check(gp, f32, "inp_g"), stream_ptr(out_g.device))
+    return gp
+
+
+def three_interpolate_grad(points, idx, weight, grad_out):
+    """tf_interpolate.py:29-34 (_three_interpolate_grad): grad_out [B,n,c] -> grad_points [B,m,c]."""
+    B, m, c = points.shape
+    n = idx.shape[1]
+    gp = torch.empty((B, m, c), dtype=f32, device=grad_out.device)
+    call("dh3d_three_interpolate_grad", B, n, c, m, check(grad_out, f32, "grad_out", 3),
+         check(idx, i32, "idx", 3), check(weight, f32, "weight", 3), check(gp, f32, "grad_points"),
+         stream_ptr(grad_out.device))
+    return gp
+
+
 def query_ball_point(radius, nsample, xyz1, xyz2):
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]

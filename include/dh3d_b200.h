@@ -223,6 +223,65 @@ DH3D_API int dh3d_netvlad(const float* features, const float* att, int B, int N,
 DH3D_API int dh3d_topk_l2(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                  int32_t* idx, float* val, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward passes and the transposed FlexConv (training side of boundary A/B)
+ *
+ * dh3d_flex_conv_grad -- replaces op FlexConvGrad
+ *   reference: user_ops/ops/flex_conv.cc:102-150, kernels/flex_conv_op.cc:57-100,
+ *   kernels/flex_conv_kernel.cc:75-163 (CPU), flex_conv_kernel_gpu.cu.cc:160-400,443-520 (GPU);
+ *   python user_ops/__init__.py:95-111.  Inputs as dh3d_flex_conv plus topdiff [B,Dout,N];
+ *   outputs grad_features [B,Din,N], grad_theta [3,Din,Dout], grad_bias [Din,Dout].  The offset is
+ *   taken from p[nbr(0,n)] (both reference backward kernels, :134 / :196-202), not from p[n].
+ *   Parameter gradients are reduced in a fixed order (deterministic); grad_features uses fp32
+ *   atomics like the reference (CudaAtomicAdd, :372).  The _pm entry takes the native layouts
+ *   (features [B,N,Din], neighborhood [B,N,K], xyz [B,N,3], topdiff [B,N,Dout]; Din, Dout % 4 == 0).
+ *
+ * dh3d_flex_pool_grad -- replaces op FlexPoolGrad (flex_pool_kernel.cc:63-95,
+ *   flex_pool_kernel_gpu.cu.cc:65-98; python :141-151): topdiff, argmax [B,D,N] -> grad_features
+ *   [B,D,N] with grad[b,d,argmax[b,d,n]] += topdiff[b,d,n].
+ *
+ * dh3d_conv_pointset_grad -- replaces op ConvPointsetGrad (conv_pointset_kernel.cc:72-147; python
+ *   :231-246): features [B,Din,N], theta [Din,Dout], neighborhood [B,K,N], topdiff [B,Dout,N] ->
+ *   grad_features [B,Din,N], grad_theta [Din,Dout], grad_bias [Dout].
+ *
+ * dh3d_flex_deconv -- replaces op FlexDeconv forward (flex_deconv_kernel.cc:25-70; python
+ *   flex_convolution_transpose :155-179): out[b,:,nbr(k,n)] += W(p[nbr(k,n)] - p[nbr(0,n)]) . f[b,:,nbr(0,n)].
+ *
+ * dh3d_group_point_grad / dh3d_gather_point_grad / dh3d_three_interpolate_grad -- replace
+ *   group_point_grad_gpu (tf_ops/grouping/tf_grouping_g.cu:114-133, launcher :195-198),
+ *   scatteraddpointKernel (tf_ops/sampling/tf_sampling_g.cu:183-192, launcher :209-211) and
+ *   threeinterpolate_grad_cpu (tf_ops/interpolation/tf_interpolate.cpp:131-153): same argument
+ *   order as the reference launchers; the output is zeroed here (the reference ops memset it in
+ *   their OpKernel, e.g. tf_grouping.cpp:188).
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API size_t dh3d_flex_conv_grad_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_conv_grad(const float* features_cm, const float* theta, const float* bias,
+                        const int32_t* neighborhood_cm, const float* positions_cm, const float* topdiff_cm,
+                        float* grad_features_cm, float* grad_theta, float* grad_bias, int B, int N, int K,
+                        int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream);
+DH3D_API size_t dh3d_flex_conv_grad_pm_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_conv_grad_pm(const float* features_pm, const float* theta, const float* bias,
+                           const int32_t* neighborhood_pm, const float* xyz_pm, const float* topdiff_pm,
+                           float* grad_features_pm, float* grad_theta, float* grad_bias, int B, int N, int K,
+                           int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream);
+DH3D_API int dh3d_flex_pool_grad(const float* topdiff_cm, const int32_t* argmax_cm, float* grad_features_cm,
+                        int B, int N, int D, void* stream);
+DH3D_API size_t dh3d_conv_pointset_grad_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_conv_pointset_grad(const float* features_cm, const float* theta, const int32_t* neighborhood_cm,
+                            const float* topdiff_cm, float* grad_features_cm, float* grad_theta,
+                            float* grad_bias, int B, int N, int K, int Din, int Dout, void* workspace,
+                            size_t workspace_bytes, void* stream);
+DH3D_API size_t dh3d_flex_deconv_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_deconv(const float* features_cm, const float* theta, const float* bias,
+                     const int32_t* neighborhood_cm, const float* positions_cm, float* out_cm, int B, int N,
+                     int K, int Din, int Dout, void* workspace, size_t workspace_bytes, void* stream);
+DH3D_API int dh3d_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out,
+                          const int32_t* idx, float* grad_points, void* stream);
+DH3D_API int dh3d_gather_point_grad(int b, int n, int m, const float* out_g, const int32_t* idx, float* inp_g,
+                           void* stream);
+DH3D_API int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
+                                const float* weight, float* grad_points, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,62 @@ def three_nn_weights(dist):
     norm = inv[..., 0:1] + inv[..., 1:2]
     norm = (norm + inv[..., 2:3]).astype(np.float32)
     return (inv / norm).astype(np.float32)
+
+
+# ---- backward passes / FlexDeconv: fp64 truth of the reference's CPU loops ---------------------
+def flex_convolution_grad(features, theta, bias, neighborhood, position, topdiff):
+    """Op-input order of FlexConvGrad (user_ops/__init__.py:95-111) -> (df, dtheta, dbias) fp64."""
+    f, th, bi = _f32(features), _f32(theta), _f32(bias)
+    nb, p, t = _i32(neighborhood), _f32(position), _f32(topdiff)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[2]
+    gf = np.empty((B, Din, N), np.float64)
+    gt = np.empty((3, Din, Dout), np.float64)
+    gb = np.empty((Din, Dout), np.float64)
+    lib().orc_flex_conv_grad(B, N, K, Din, Dout, _p(f), _p(th), _p(bi), _p(nb), _p(p), _p(t),
+                             _p(gf), _p(gt), _p(gb))
+    return gf, gt, gb
+
+
+def flex_pooling_grad(topdiff, argmax):
+    t, a = _f32(topdiff), _i32(argmax)
+    B, D, N = t.shape
+    gf = np.empty((B, D, N), np.float64)
+    lib().orc_flex_pool_grad(B, N, D, _p(t), _p(a), _p(gf))
+    return gf
+
+
+def convolution_pointset_grad(features, theta, neighborhood, topdiff):
+    f, th, nb, t = _f32(features), _f32(theta), _i32(neighborhood), _f32(topdiff)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[1]
+    gf = np.empty((B, Din, N), np.float64)
+    gt = np.empty((Din, Dout), np.float64)
+    gb = np.empty((Dout,), np.float64)
+    lib().orc_conv_pointset_grad(B, N, K, Din, Dout, _p(f), _p(th), _p(nb), _p(t), _p(gf), _p(gt), _p(gb))
+    return gf, gt, gb
+
+
+def flex_convolution_transpose(features, position, neighborhood, theta, bias):
+    f, p, nb, th, bi = _f32(features), _f32(position), _i32(neighborhood), _f32(theta), _f32(bias)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[2]
+    out = np.empty((B, Dout, N), np.float64)
+    lib().orc_flex_deconv(B, N, K, Din, Dout, _p(f), _p(th), _p(bi), _p(nb), _p(p), _p(out))
+    return out
+
+
+def group_point_grad(n, grad_out, idx):
+    g, i = _f32(grad_out), _i32(idx)
+    B, M, S, C = g.shape
+    gp = np.empty((B, n, C), np.float64)
+    lib().orc_group_point_grad(B, int(n), C, M, S, _p(g), _p(i), _p(gp))
+    return gp
+
+
+def three_interpolate_grad(m, grad_out, idx, weight):
+    g, i, w = _f32(grad_out), _i32(idx), _f32(weight)
+    B, N, C = g.shape
+    gp = np.empty((B, int(m), C), np.float64)
+    lib().orc_three_interpolate_grad(B, N, C, int(m), _p(g), _p(i), _p(w), _p(gp))
+    return gp

@@ -2,12 +2,13 @@
 into oracle/_ref/ (git-ignored; travels to the GPU box with the snapshot).  Test/bench
 infrastructure only -- see oracle/__init__.py.
 
-  libdh3d_ref_cuda.so  user_ops/kernels/{knn_bruteforce,flex_conv,flex_pool,conv_pointset}_kernel_gpu.cu.cc
+  libdh3d_ref_cuda.so  user_ops/kernels/{knn_bruteforce,flex_conv,flex_pool,conv_pointset,flex_deconv}_kernel_gpu.cu.cc
                        + tf_ops/sampling/tf_sampling_g.cu + tf_ops/grouping/tf_grouping_g.cu, built
                        for sm_100a with the reference's own flags (-O3 / -O2, no fast-math;
                        user_ops/CMakeLists.txt:32, tf_ops/*/tf_*_compile.sh) against a stub of the two
                        TensorFlow headers they include (oracle/ref_shim/stub), CUDA 12.9's bundled CUB.
-  libdh3d_ref_cpu.so   user_ops/kernels/{flex_conv,flex_pool,conv_pointset}_kernel.cc (CPU functors)
+  libdh3d_ref_cpu.so   user_ops/kernels/{flex_conv,flex_pool,conv_pointset,flex_deconv}_kernel.cc (CPU functors,
+                       forward and Grad)
                        + the plain-C functions of tf_ops/interpolation/tf_interpolate.cpp (lines
                        55-153 are extracted at BUILD time into oracle/_ref/; that file also holds
                        TF op registrations that cannot compile without TensorFlow), g++ -O2, no -mfma
@@ -40,12 +41,17 @@ def _gxx():
     return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
+def _fresh(so, shim_src):
+    """The prebuilt library is kept unless the shim that defines its entry points is newer."""
+    return os.path.exists(so) and os.path.getmtime(so) >= os.path.getmtime(os.path.join(SHIM, shim_src))
+
+
 def build_cuda(force=False):
-    if os.path.exists(CUDA_SO) and not force:
+    if _fresh(CUDA_SO, "ref_cuda_shim.cu") and not force:
         return CUDA_SO
     kern = os.path.join(REF, "user_ops", "kernels")
     objs = []
-    for name in ("knn_bruteforce", "flex_conv", "flex_pool", "conv_pointset"):
+    for name in ("knn_bruteforce", "flex_conv", "flex_pool", "conv_pointset", "flex_deconv"):
         obj = os.path.join(OUT, name + "_gpu.o")
         _run(["nvcc"] + ARCH + ["-O3", "-std=c++17", "--expt-relaxed-constexpr", "-DGOOGLE_CUDA=1", "-w",
                                 "-I", STUB, "-I", kern, "-Xcompiler", "-fPIC", "-x", "cu", "-c",
@@ -65,7 +71,7 @@ def build_cuda(force=False):
 
 
 def build_cpu(force=False):
-    if os.path.exists(CPU_SO) and not force:
+    if _fresh(CPU_SO, "ref_cpu_shim.cpp") and not force:
         return CPU_SO
     kern = os.path.join(REF, "user_ops", "kernels")
     # the plain-C functions of tf_interpolate.cpp (threenn_cpu .. threeinterpolate_grad_cpu)
@@ -81,7 +87,7 @@ def build_cpu(force=False):
     o = os.path.join(OUT, "tf_interpolate_fns.o")
     _run([_gxx(), "-std=c++11", "-O2", "-fPIC", "-c", extracted, "-o", o])
     objs.append(o)
-    for name in ("flex_conv", "flex_pool", "conv_pointset"):
+    for name in ("flex_conv", "flex_pool", "conv_pointset", "flex_deconv"):
         o = os.path.join(OUT, name + "_cpu.o")
         _run([_gxx(), "-std=c++14", "-O3", "-fPIC", "-w", "-I", STUB, "-I", kern, "-c",
               os.path.join(kern, name + "_kernel.cc"), "-o", o])

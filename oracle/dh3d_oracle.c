@@ -494,3 +494,144 @@ ORC_API void orc_three_interpolate(int B, int m, int c, int n, const float* poin
     }
   }
 }
+
+/* ==========================================================================================
+ * Backward passes and FlexDeconv.  The GPU results are checked at a tolerance
+ * (fp32 atomics have no fixed summation order, in the reference as here), so these restatements
+ * accumulate in DOUBLE: they are the fp64 truth of the reference's CPU loops.
+ * ========================================================================================== */
+
+/* FlexConvGrad (user_ops/kernels/flex_conv_kernel.cc:75-163): three loop nests over (b,n,k_,j,l):
+ *   grad_bias(j,l)   += f(b,j,k) * top(b,l,n)                                     (:108-119)
+ *   grad_theta(i,j,l)+= f(b,j,k) * (p(b,i,k) - p(b,i,nbr(b,0,n))) * top(b,l,n)    (:122-139)
+ *   grad_f(b,j,k)    += (bias(j,l) + sum_i theta(i,j,l)*delta_i) * top(b,l,n)     (:142-159)
+ * with k = nbr(b,k_,n).  The CUDA kernels use the same centre nbr(0,n)
+ * (flex_conv_kernel_gpu.cu.cc:196-202,313-318). */
+ORC_API void orc_flex_conv_grad(int B, int N, int K, int Din, int Dout, const float* f, const float* theta,
+                                const float* bias, const int32_t* nbr, const float* pos, const float* top,
+                                double* gf, double* gtheta, double* gbias) {
+  memset(gf, 0, sizeof(double) * (size_t)B * Din * N);
+  memset(gtheta, 0, sizeof(double) * (size_t)3 * Din * Dout);
+  memset(gbias, 0, sizeof(double) * (size_t)Din * Dout);
+  for (int b = 0; b < B; ++b)
+    for (int n = 0; n < N; ++n) {
+      const int c0 = nbr[((size_t)b * K + 0) * N + n];
+      for (int k_ = 0; k_ < K; ++k_) {
+        const int k = nbr[((size_t)b * K + k_) * N + n];
+        double delta[3];
+        for (int i = 0; i < 3; ++i)
+          delta[i] = (double)(float)(pos[((size_t)b * 3 + i) * N + k] - pos[((size_t)b * 3 + i) * N + c0]);
+        for (int j = 0; j < Din; ++j) {
+          const double fv = f[((size_t)b * Din + j) * N + k];
+          double acc = 0.0;
+          for (int l = 0; l < Dout; ++l) {
+            const double t = top[((size_t)b * Dout + l) * N + n];
+            gbias[(size_t)j * Dout + l] += fv * t;
+            double W = bias[(size_t)j * Dout + l];
+            for (int i = 0; i < 3; ++i) {
+              gtheta[((size_t)i * Din + j) * Dout + l] += fv * delta[i] * t;
+              W += (double)theta[((size_t)i * Din + j) * Dout + l] * delta[i];
+            }
+            acc += W * t;
+          }
+          gf[((size_t)b * Din + j) * N + k] += acc;
+        }
+      }
+    }
+}
+
+/* FlexPoolGrad (flex_pool_kernel.cc:63-95): grad_f(b,d,argmax(b,d,n)) += top(b,d,n). */
+ORC_API void orc_flex_pool_grad(int B, int N, int D, const float* top, const int32_t* argmax, double* gf) {
+  memset(gf, 0, sizeof(double) * (size_t)B * D * N);
+  for (int b = 0; b < B; ++b)
+    for (int d = 0; d < D; ++d)
+      for (int n = 0; n < N; ++n) {
+        const size_t e = ((size_t)b * D + d) * N + n;
+        gf[((size_t)b * D + d) * N + argmax[e]] += top[e];
+      }
+}
+
+/* ConvPointsetGrad (conv_pointset_kernel.cc:72-147):
+ *   grad_bias(l)    += top(b,l,n)                                                  (:100-108)
+ *   grad_theta(j,l) += (f(b,j,k) - f(b,j,nbr(0,n))) * top(b,l,n)                   (:111-126)
+ *   grad_f(b,j,k)   += theta(j,l)*top(b,l,n);  grad_f(b,j,nbr(0,n)) -= the same    (:130-144) */
+ORC_API void orc_conv_pointset_grad(int B, int N, int K, int Din, int Dout, const float* f, const float* theta,
+                                    const int32_t* nbr, const float* top, double* gf, double* gtheta,
+                                    double* gbias) {
+  memset(gf, 0, sizeof(double) * (size_t)B * Din * N);
+  memset(gtheta, 0, sizeof(double) * (size_t)Din * Dout);
+  memset(gbias, 0, sizeof(double) * (size_t)Dout);
+  for (int b = 0; b < B; ++b)
+    for (int n = 0; n < N; ++n) {
+      for (int l = 0; l < Dout; ++l) gbias[l] += top[((size_t)b * Dout + l) * N + n];
+      const int c0 = nbr[((size_t)b * K + 0) * N + n];
+      for (int k_ = 0; k_ < K; ++k_) {
+        const int k = nbr[((size_t)b * K + k_) * N + n];
+        for (int j = 0; j < Din; ++j) {
+          const double df = (double)(float)(f[((size_t)b * Din + j) * N + k] - f[((size_t)b * Din + j) * N + c0]);
+          for (int l = 0; l < Dout; ++l) {
+            const double t = top[((size_t)b * Dout + l) * N + n];
+            gtheta[(size_t)j * Dout + l] += df * t;
+            const double v = (double)theta[(size_t)j * Dout + l] * t;
+            gf[((size_t)b * Din + j) * N + k] += v;
+            gf[((size_t)b * Din + j) * N + c0] -= v;
+          }
+        }
+      }
+    }
+}
+
+/* FlexDeconv forward (flex_deconv_kernel.cc:25-70): self = nbr(0,n), other = nbr(k_,n):
+ *   out(b,dout,other) += (bias(din,dout) + sum_dp theta(dp,din,dout)*(p(other)-p(self))) * f(b,din,self). */
+ORC_API void orc_flex_deconv(int B, int N, int K, int Din, int Dout, const float* f, const float* theta,
+                             const float* bias, const int32_t* nbr, const float* pos, double* out) {
+  memset(out, 0, sizeof(double) * (size_t)B * Dout * N);
+  for (int b = 0; b < B; ++b)
+    for (int n = 0; n < N; ++n) {
+      const int self_k = nbr[((size_t)b * K + 0) * N + n];
+      for (int k_ = 0; k_ < K; ++k_) {
+        const int other = nbr[((size_t)b * K + k_) * N + n];
+        double delta[3];
+        for (int i = 0; i < 3; ++i)
+          delta[i] = (double)(float)(pos[((size_t)b * 3 + i) * N + other] - pos[((size_t)b * 3 + i) * N + self_k]);
+        for (int dout = 0; dout < Dout; ++dout) {
+          double acc = 0.0;
+          for (int din = 0; din < Din; ++din) {
+            double W = bias[(size_t)din * Dout + dout];
+            for (int i = 0; i < 3; ++i) W += (double)theta[((size_t)i * Din + din) * Dout + dout] * delta[i];
+            acc += W * (double)f[((size_t)b * Din + din) * N + self_k];
+          }
+          out[((size_t)b * Dout + dout) * N + other] += acc;
+        }
+      }
+    }
+}
+
+/* group_point_grad_gpu (tf_ops/grouping/tf_grouping_g.cu:114-133): grad_points[b,idx[b,j,k],:] += grad_out[b,j,k,:];
+ * scatteraddpointKernel (tf_ops/sampling/tf_sampling_g.cu:183-192) is the c = 3, nsample = 1 case. */
+ORC_API void orc_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out, const int32_t* idx,
+                                  double* grad_points) {
+  memset(grad_points, 0, sizeof(double) * (size_t)b * n * c);
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < m; ++j)
+      for (int k = 0; k < nsample; ++k) {
+        const int ii = idx[((size_t)i * m + j) * nsample + k];
+        for (int l = 0; l < c; ++l)
+          grad_points[((size_t)i * n + ii) * c + l] += grad_out[(((size_t)i * m + j) * nsample + k) * c + l];
+      }
+}
+
+/* threeinterpolate_grad_cpu (tf_ops/interpolation/tf_interpolate.cpp:131-153):
+ * grad_points[b,idx[b,j,t],:] += grad_out[b,j,:] * weight[b,j,t], t = 0..2. */
+ORC_API void orc_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
+                                        const float* weight, double* grad_points) {
+  memset(grad_points, 0, sizeof(double) * (size_t)b * m * c);
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < n; ++j)
+      for (int t = 0; t < 3; ++t) {
+        const int ii = idx[((size_t)i * n + j) * 3 + t];
+        const double w = weight[((size_t)i * n + j) * 3 + t];
+        for (int l = 0; l < c; ++l)
+          grad_points[((size_t)i * m + ii) * c + l] += (double)grad_out[((size_t)i * n + j) * c + l] * w;
+      }
+}

@@ -185,3 +185,125 @@ def cuda_conv_pointset(features, neighborhood, theta, bias):
     _chk(cuda().ref_conv_pointset(B, N, K, Din, Dout, _d(features.contiguous()), _d(theta.contiguous()),
                                   _d(bias.contiguous()), _d(neighborhood.contiguous()), _d(out)), "conv_pointset")
     return out
+
+
+# ---- backward passes / FlexDeconv: reference CPU functors ----------------------------------------
+def cpu_flex_conv_grad(features, theta, bias, neighborhood, position, topdiff):
+    f, th, bi = _np(features, np.float32), _np(theta, np.float32), _np(bias, np.float32)
+    nb, p, t = _np(neighborhood, np.int32), _np(position, np.float32), _np(topdiff, np.float32)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[2]
+    gf, gt, gb = np.empty((B, Din, N), np.float32), np.empty((3, Din, Dout), np.float32), np.empty((Din, Dout), np.float32)
+    cpu().ref_cpu_flex_conv_grad(B, N, K, Din, Dout, _p(f), _p(th), _p(bi), _p(nb), _p(p), _p(t), _p(gf), _p(gt), _p(gb))
+    return gf, gt, gb
+
+
+def cpu_flex_pool_grad(features, neighborhood, topdiff, argmax):
+    f, nb = _np(features, np.float32), _np(neighborhood, np.int32)
+    t, a = _np(topdiff, np.float32), _np(argmax, np.int32)
+    B, D, N = f.shape
+    gf = np.empty((B, D, N), np.float32)
+    cpu().ref_cpu_flex_pool_grad(B, N, nb.shape[1], D, _p(f), _p(nb), _p(t), _p(a), _p(gf))
+    return gf
+
+
+def cpu_conv_pointset_grad(features, theta, bias, neighborhood, topdiff):
+    f, th, bi = _np(features, np.float32), _np(theta, np.float32), _np(bias, np.float32)
+    nb, t = _np(neighborhood, np.int32), _np(topdiff, np.float32)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[1]
+    gf, gt, gb = np.empty((B, Din, N), np.float32), np.empty((Din, Dout), np.float32), np.empty((Dout,), np.float32)
+    cpu().ref_cpu_conv_pointset_grad(B, N, K, Din, Dout, _p(f), _p(th), _p(bi), _p(nb), _p(t), _p(gf), _p(gt), _p(gb))
+    return gf, gt, gb
+
+
+def cpu_flex_deconv(features, position, neighborhood, theta, bias):
+    f, p, nb = _np(features, np.float32), _np(position, np.float32), _np(neighborhood, np.int32)
+    th, bi = _np(theta, np.float32), _np(bias, np.float32)
+    B, Din, N = f.shape
+    K, Dout = nb.shape[1], th.shape[2]
+    out = np.empty((B, Dout, N), np.float32)
+    cpu().ref_cpu_flex_deconv(B, N, K, Din, Dout, _p(f), _p(th), _p(bi), _p(nb), _p(p), _p(out))
+    return out
+
+
+def cpu_three_interpolate_grad(m, grad_out, idx, weight):
+    g, i, w = _np(grad_out, np.float32), _np(idx, np.int32), _np(weight, np.float32)
+    B, n, c = g.shape
+    gp = np.zeros((B, int(m), c), np.float32)
+    cpu().ref_cpu_three_interpolate_grad(B, n, c, int(m), _p(g), _p(i), _p(w), _p(gp))
+    return gp
+
+
+# ---- backward passes / FlexDeconv: reference CUDA kernels ----------------------------------------
+def cuda_flex_conv_grad(features, theta, bias, neighborhood, position, topdiff):
+    import torch
+    B, Din, N = features.shape
+    K, Dout = neighborhood.shape[1], theta.shape[2]
+    dev = features.device
+    gf = torch.empty((B, Din, N), dtype=torch.float32, device=dev)
+    gt = torch.empty((3, Din, Dout), dtype=torch.float32, device=dev)
+    gb = torch.empty((Din, Dout), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_flex_conv_grad(B, N, K, Din, Dout, _d(features.contiguous()), _d(theta.contiguous()),
+                                   _d(bias.contiguous()), _d(neighborhood.contiguous()), _d(position.contiguous()),
+                                   _d(topdiff.contiguous()), _d(gf), _d(gt), _d(gb)), "flex_conv_grad")
+    return gf, gt, gb
+
+
+def cuda_flex_pool_grad(features, neighborhood, topdiff, argmax):
+    import torch
+    B, D, N = features.shape
+    gf = torch.empty((B, D, N), dtype=torch.float32, device=features.device)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_flex_pool_grad(B, N, neighborhood.shape[1], D, _d(features.contiguous()),
+                                   _d(neighborhood.contiguous()), _d(topdiff.contiguous()), _d(argmax.contiguous()),
+                                   _d(gf)), "flex_pool_grad")
+    return gf
+
+
+def cuda_conv_pointset_grad(features, theta, bias, neighborhood, topdiff):
+    import torch
+    B, Din, N = features.shape
+    K, Dout = neighborhood.shape[1], theta.shape[1]
+    dev = features.device
+    gf = torch.empty((B, Din, N), dtype=torch.float32, device=dev)
+    gt = torch.empty((Din, Dout), dtype=torch.float32, device=dev)
+    gb = torch.empty((Dout,), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_conv_pointset_grad(B, N, K, Din, Dout, _d(features.contiguous()), _d(theta.contiguous()),
+                                       _d(bias.contiguous()), _d(neighborhood.contiguous()), _d(topdiff.contiguous()),
+                                       _d(gf), _d(gt), _d(gb)), "conv_pointset_grad")
+    return gf, gt, gb
+
+
+def cuda_flex_deconv(features, position, neighborhood, theta, bias):
+    import torch
+    B, Din, N = features.shape
+    K, Dout = neighborhood.shape[1], theta.shape[2]
+    out = torch.empty((B, Dout, N), dtype=torch.float32, device=features.device)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_flex_deconv(B, N, K, Din, Dout, _d(features.contiguous()), _d(theta.contiguous()),
+                                _d(bias.contiguous()), _d(neighborhood.contiguous()), _d(position.contiguous()),
+                                _d(out)), "flex_deconv")
+    return out
+
+
+def cuda_group_point_grad(n, grad_out, idx):
+    import torch
+    B, M, S, C = grad_out.shape
+    gp = torch.empty((B, int(n), C), dtype=torch.float32, device=grad_out.device)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_group_point_grad(B, int(n), C, M, S, _d(grad_out.contiguous()), _d(idx.contiguous()), _d(gp)),
+         "group_point_grad")
+    return gp
+
+
+def cuda_gather_point_grad(n, out_g, idx):
+    import torch
+    B, M, _ = out_g.shape
+    gp = torch.empty((B, int(n), 3), dtype=torch.float32, device=out_g.device)
+    torch.cuda.synchronize()
+    _chk(cuda().ref_gather_point_grad(B, int(n), M, _d(out_g.contiguous()), _d(idx.contiguous()), _d(gp)),
+         "gather_point_grad")
+    return gp

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "dh3d_group_point_grad": (_c_int, [_c_int] * 5 + [_p, _p, _p, _p]),
     "dh3d_gather_point_grad": (_c_int, [_c_int] * 3 + [_p, _p, _p, _p]),
     "dh3d_three_interpolate_grad": (_c_int, [_c_int] * 4 + [_p] * 5),
+    "dh3d_keypoint_nms_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "dh3d_keypoint_nms": (_c_int, [_p, _p, _c_int, _c_int, _c_float, _c_float, _c_int, _c_int, _p, _p, _p,
+                                   _c_size_t, _p]),
 }
 
 _lib = None
@@ -80,6 +83,7 @@ _KERNELS_PER_CALL = {
     "dh3d_flex_conv_pm": 3,                                          # theta_ext + moments + gemm (+1 if feature_bias)
     "dh3d_query_ball_point": 2, "dh3d_netvlad": 4, "dh3d_three_nn_ws": 3,
     "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
+    "dh3d_keypoint_nms": 5,
 }
 
 

@@ -97,6 +97,11 @@ int group_point_grad_launch(int b, int n, int c, int m, int nsample, const float
                             float* grad_points, cudaStream_t st);
 int three_interpolate_grad_launch(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
                                   const float* weight, float* grad_points, cudaStream_t st);
+// nms.cu
+size_t keypoint_nms_workspace_bytes(int B, int N);
+int keypoint_nms_launch(const float* xyz, const float* attention, int B, int N, float nms_radius,
+                        float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
+                        int32_t* out_cnt, void* ws, size_t ws_bytes, cudaStream_t st);
 // topk.cu
 int topk_l2_launch(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                    int32_t* idx, float* val, cudaStream_t st);
@@ -376,6 +381,14 @@ int dh3d_gather_point_grad(int b, int n, int m, const float* out_g, const int32_
 int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
                                 const float* weight, float* grad_points, void* stream) {
   return three_interpolate_grad_launch(b, n, c, m, grad_out, idx, weight, grad_points, S(stream));
+}
+
+size_t dh3d_keypoint_nms_workspace_bytes(int B, int N) { return keypoint_nms_workspace_bytes(B, N); }
+int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int B, int N, float nms_radius,
+                      float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
+                      int32_t* out_cnt, void* workspace, size_t workspace_bytes, void* stream) {
+  return keypoint_nms_launch(xyz_pm, attention, B, N, nms_radius, min_response_ratio, max_keypoints, remove_noise,
+                             out_idx, out_cnt, workspace, workspace_bytes, S(stream));
 }
 
 }  // extern "C"

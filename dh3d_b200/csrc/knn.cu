@@ -421,7 +421,7 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
     return knn_tiled_launch(pos, B, N, K, sb, sp, sd, ids, dists, workspace, workspace_bytes, st);
   if (!pos || !ids || !dists) return DH3D_ERR_NULL;
   if (B <= 0 || N <= 0 || K <= 0) return DH3D_ERR_DIM;
-  if (K > 32 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
+  if (K > 64 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < knn_workspace_bytes(B, N)) return DH3D_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 127) != 0) return DH3D_ERR_ALIGN;
   const KnnOrder o = knn_order(N);
@@ -444,7 +444,8 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   else if (K <= 4) DH3D_KNN(4, false);
   else if (K <= 8) DH3D_KNN(8, false);
   else if (K <= 16) DH3D_KNN(16, false);
-  else DH3D_KNN(32, false);
+  else if (K <= 32) DH3D_KNN(32, false);
+  else DH3D_KNN(64, false);   // keypoint NMS uses K = 50 (core/utils.py:17)
 #undef DH3D_KNN
   return launch_status();
 }

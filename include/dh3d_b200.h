@@ -55,7 +55,7 @@ DH3D_API const char* dh3d_error_string(int code); /* static string for a DH3D_ER
  *   kernels/knn_bruteforce_kernel_gpu.cu.cc:45-134,162-228; python user_ops/__init__.py:50.
  *   positions [B,3,N] cm (or [B,N,3] pm for the _pm entry) -> ids [B,N,K] i32 (self included,
  *   ascending Euclidean distance, ties in the reference's BlockRadixSort blocked order), dists
- *   [B,N,K] f32 (sqrt'ed).  K in [1,32]; N in [1, 65536]; Dp must be 3 (the only value DH3D uses).
+ *   [B,N,K] f32 (sqrt'ed).  K in [1,64]; N in [1, 65536]; Dp must be 3 (the only value DH3D uses).
  *   Unlike the reference there is no N <= 8192 cap (kernel_gpu.cu.cc:213-221); for N > 8192 the
  *   tie order is plain index order.
  * ------------------------------------------------------------------------------------------- */
@@ -281,6 +281,20 @@ DH3D_API int dh3d_gather_point_grad(int b, int n, int m, const float* out_g, con
                            void* stream);
 DH3D_API int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
                                 const float* weight, float* grad_points, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Keypoint NMS on the detector attention -- replaces core/utils.py:15-43 `single_nms` (host numpy +
+ *   sklearn ball tree; caller evaluate/local_eval/localdesc_extract.py:92-98), batched over clouds.
+ *   xyz [B,N,3] pm, attention [B,N] -> out_idx [B,max_keypoints] i32 (descending (attention, index)
+ *   order, padded with -1), out_cnt [B] i32 = min(#local maxima above the response threshold, max_keypoints).
+ *   50-NN lists from the k-NN engine; radius / noise thresholds are evaluated on fp64 pair distances
+ *   (sklearn's arithmetic).  remove_noise != 0 zeroes the attention of points whose 8th neighbour is
+ *   farther than 2.0 (:19-22).  N >= 50.  `attention` is not modified (the reference mutates it).
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API size_t dh3d_keypoint_nms_workspace_bytes(int B, int N);
+DH3D_API int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int B, int N, float nms_radius,
+                      float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
+                      int32_t* out_cnt, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

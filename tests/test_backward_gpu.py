@@ -74,8 +74,9 @@ def test_flex_conv_grad_pm_entry():
     gt, gb = torch.empty((3, Din, Dout), device="cuda"), torch.empty((Din, Dout), device="cuda")
     ws, wp, wn = workspace(query("dh3d_flex_conv_grad_pm_workspace_bytes", B, N, K, Din, Dout), gf.device)
     f32, i32 = torch.float32, torch.int32
-    call("dh3d_flex_conv_grad_pm", check(pm(f), f32, "f"), check(cu(th), f32, "t"), check(cu(bi), f32, "b"),
-         check(pm(nb), i32, "n"), check(pm(pos), f32, "p"), check(pm(top), f32, "g"), check(gf, f32, "gf"),
+    f_pm, nb_pm, pos_pm, top_pm, th_d, bi_d = pm(f), pm(nb), pm(pos), pm(top), cu(th), cu(bi)   # kept alive
+    call("dh3d_flex_conv_grad_pm", check(f_pm, f32, "f"), check(th_d, f32, "t"), check(bi_d, f32, "b"),
+         check(nb_pm, i32, "n"), check(pos_pm, f32, "p"), check(top_pm, f32, "g"), check(gf, f32, "gf"),
          check(gt, f32, "gt"), check(gb, f32, "gb"), B, N, K, Din, Dout, wp, wn, stream_ptr(gf.device))
     assert rel(gf.transpose(1, 2), a[0].cpu().numpy()) < TOL
     assert torch.equal(gt, a[1]) and torch.equal(gb, a[2])

@@ -36,7 +36,7 @@ def close(actual, expected, rel=REL):
 
 # ------------------------------------------------------------------------------------------ kNN
 @pytest.mark.parametrize("B,N,K", [(1, 4, 4), (2, 32, 4), (1, 1024, 8), (2, 2000, 8), (2, 4096, 16),
-                                   (2, 8192, 8), (1, 8192, 32), (3, 100, 5), (1, 700, 1)])
+                                   (2, 8192, 8), (1, 8192, 32), (3, 100, 5), (1, 700, 1), (2, 3000, 50), (1, 400, 64)])
 def test_knn_bitexact_random(B, N, K):
     from dh3d_b200 import user_ops
     rng = np.random.RandomState(B * 131 + N + K)

@@ -41,7 +41,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.dh3d_knn_bruteforce(null, 1, 3, 8, 2, one, one, one, 1 << 20, null) == -1
     assert lib.dh3d_knn_bruteforce(one, 1, 3, 0, 2, one, one, one, 1 << 20, null) == -2
     assert lib.dh3d_knn_bruteforce(one, 1, 2, 8, 2, one, one, one, 1 << 20, null) == -3   # Dp != 3
-    assert lib.dh3d_knn_bruteforce(one, 1, 3, 8, 64, one, one, one, 1 << 20, null) == -3  # K > 32
+    assert lib.dh3d_knn_bruteforce(one, 1, 3, 8, 65, one, one, one, 1 << 20, null) == -3  # K > 64
     assert lib.dh3d_knn_bruteforce(one, 1, 3, 8, 2, one, one, one, 16, null) == -4        # workspace
     assert lib.dh3d_farthest_point_sample(0, 8, 2, one, one, null) == -2
     assert lib.dh3d_farthest_point_sample(1, 8, 0, one, one, null) == 0                    # m == 0: no-op
@@ -50,6 +50,17 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.dh3d_conv_pointset(one, one, one, one, one, 1, 8, 4, 65, 8, null) == -3      # Din > 64
     assert lib.dh3d_linear(one, 6, one, null, null, 0, one, 8, 4, 6, 8, null) == -2         # K % 4
     assert lib.dh3d_three_nn(1, 0, 4, one, one, one, one, null) == -2
+    # backward passes / deconv / NMS
+    assert lib.dh3d_flex_conv_grad(one, one, one, one, one, one, one, one, null, 1, 8, 4, 6, 8, one, 1 << 30, null) == -1
+    assert lib.dh3d_flex_conv_grad(one, one, one, one, one, one, one, one, one, 1, 8, 4, 6, 8, one, 16, null) == -4
+    assert lib.dh3d_flex_conv_grad_pm(one, one, one, one, one, one, one, one, one, 1, 8, 4, 6, 8, one, 1 << 30, null) == -3
+    assert lib.dh3d_flex_pool_grad(one, one, one, 1, 0, 4, null) == -2
+    assert lib.dh3d_conv_pointset_grad(one, one, one, one, one, one, one, 1, 8, 4, 3, 32, one, 16, null) == -4
+    assert lib.dh3d_flex_deconv(one, one, one, one, one, one, 0, 8, 4, 6, 8, one, 1 << 30, null) == -2
+    assert lib.dh3d_group_point_grad(1, 8, 4, 0, 1, one, one, one, null) == -2
+    assert lib.dh3d_three_interpolate_grad(1, 8, 4, 2, one, one, null, one, null) == -1
+    assert lib.dh3d_keypoint_nms(one, one, 1, 40, 0.5, 0.01, 16, 1, one, one, one, 1 << 30, null) == -3   # N < 50
+    assert lib.dh3d_keypoint_nms(one, one, 1, 400, 0.5, 0.01, 16, 1, one, one, one, 16, null) == -4
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 128, 64, 256) == 0                      # unsupported dims
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 256, 64, 256) > 0
 

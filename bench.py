@@ -141,7 +141,8 @@ def synth_clouds(batch, n_points, seed):
     """xyz ~ U(-25, 25)^3 fp32, torch.Generator().manual_seed(1234 + id)."""
     import torch
     g = torch.Generator().manual_seed(1234 + seed)
-    return (torch.rand((batch, n_points, 3), generator=g) * 50.0 - 25.0).float()
+    pts = (torch.rand((batch, n_points, 3), generator=g) * 50.0 - 25.0).float()
+    return pts
 
 
 def algorithmic(tag, name):
@@ -175,10 +176,10 @@ def algorithmic(tag, name):
 OP_KERNEL = {
     "dh3d_linear_rowdot_packed": ("gemm_tc16_kernel", "gemm_tc_kernel"),
     "dh3d_linear_packed": ("gemm_tc16_kernel", "gemm_tc_kernel"),
-    "dh3d_netvlad": ("netvlad_aggregate_kernel",),
+    "dh3d_netvlad": ("netvlad_tc_kernel", "netvlad_aggregate_kernel"),
     "dh3d_knn_bruteforce_pm": ("knn_query_kernel<8, 1, 1",),
-    "dh3d_farthest_point_sample": ("fps_reg_kernel",),
-    "dh3d_flex_conv_pm": ("flexconv_tc_kernel",),
+    "dh3d_farthest_point_sample": ("fps_cluster_kernel", "fps_reg_kernel"),
+    "dh3d_flex_conv_pm": ("flexconv_ca_kernel", "flexconv_tc_kernel"),
 }
 
 

@@ -118,6 +118,57 @@ def main(out_path):
     r = timeit(lambda: ref.cuda_group_point(f128, kp), 1, 3) if have_ref else None
     rows.append({"op": "group_point", "B": B, "N": N, "M": 1024, "C": 128, "ms": mine, "ref_cuda_ms": r,
                  "speedup": (r / mine) if r else None})
+    # ---- backward passes / FlexDeconv / NMS, DH3D layer shapes at 8 clouds ----
+    from dh3d_b200 import utils as dutils
+    Bb = 8
+    ptsb, nbrb = pts[:Bb].contiguous(), nbr[:Bb].contiguous()
+    pcb, ncb = ptsb.transpose(1, 2).contiguous(), nbrb.transpose(1, 2).contiguous()
+    for (ci, co) in ((32, 64), (64, 64)):
+        fcb = torch.randn((Bb, ci, N), device="cuda", generator=g)
+        th = torch.randn((3, ci, co), device="cuda", generator=g) / ci ** 0.5
+        bi = torch.randn((ci, co), device="cuda", generator=g) / ci ** 0.5
+        top = torch.randn((Bb, co, N), device="cuda", generator=g)
+        mine = timeit(lambda: user_ops.flex_convolution_grad(fcb, th, bi, ncb, pcb, top))
+        r = timeit(lambda: ref.cuda_flex_conv_grad(fcb, th, bi, ncb, pcb, top), 1, 2) if have_ref else None
+        n = Bb * N
+        byts = 4.0 * (2 * n * ci + n * co + n * 8 + 3 * n + 2 * 4 * ci * co)   # f, top, nbr, xyz in; grad_f out; params
+        rows.append({"op": "flex_conv_grad", "B": Bb, "N": N, "K": 8, "Cin": ci, "Cout": co, "ms": mine,
+                     "ref_cuda_ms": r, "speedup": (r / mine) if r else None, "algorithmic_GBs": byts / mine / 1e6,
+                     "frac_of_hbm_peak": byts / mine / 1e6 / hbm,
+                     "note": "reference-layout entry (4 layout transposes inside the timed call)"})
+        mine = timeit(lambda: user_ops.flex_convolution_transpose(fcb, pcb, ncb, th, bi))
+        r = timeit(lambda: ref.cuda_flex_deconv(fcb, pcb, ncb, th, bi), 1, 2) if have_ref else None
+        rows.append({"op": "flex_deconv", "B": Bb, "N": N, "K": 8, "Cin": ci, "Cout": co, "ms": mine,
+                     "ref_cuda_ms": r, "speedup": (r / mine) if r else None})
+    fcb = torch.randn((Bb, 64, N), device="cuda", generator=g)
+    top = torch.randn((Bb, 64, N), device="cuda", generator=g)
+    _, arg = user_ops.flex_pooling(fcb, ncb)
+    mine = timeit(lambda: user_ops.flex_pooling_grad(fcb, ncb, top, arg))
+    r = timeit(lambda: ref.cuda_flex_pool_grad(fcb, ncb, top, arg), 1, 3) if have_ref else None
+    rows.append({"op": "flex_pool_grad", "B": Bb, "N": N, "D": 64, "ms": mine, "ref_cuda_ms": r,
+                 "speedup": (r / mine) if r else None, "algorithmic_GBs": 4.0 * 3 * Bb * N * 64 / mine / 1e6})
+    th2c, top32 = th2.contiguous(), torch.randn((Bb, 32, N), device="cuda", generator=g)
+    mine = timeit(lambda: user_ops.convolution_pointset_grad(pcb, th2c, bi2, ncb, top32))
+    r = timeit(lambda: ref.cuda_conv_pointset_grad(pcb, th2c, bi2, ncb, top32), 1, 2) if have_ref else None
+    rows.append({"op": "conv_pointset_grad", "B": Bb, "N": N, "ms": mine, "ref_cuda_ms": r,
+                 "speedup": (r / mine) if r else None})
+    go = torch.randn((B, 1024, 1, 128), device="cuda", generator=g)
+    mine = timeit(lambda: tf_ops.group_point_grad(f128, kp, go))
+    r = timeit(lambda: ref.cuda_group_point_grad(N, go, kp), 1, 3) if have_ref else None
+    rows.append({"op": "group_point_grad", "B": B, "N": N, "M": 1024, "C": 128, "ms": mine, "ref_cuda_ms": r,
+                 "speedup": (r / mine) if r else None})
+    known = torch.randn((B, 1024, 128), device="cuda", generator=g)
+    d3, i3 = tf_ops.three_nn(pts, tf_ops.gather_point(pts, kp.squeeze(2).contiguous()))
+    w3 = torch.softmax(-d3, dim=2).contiguous()
+    mine = timeit(lambda: tf_ops.three_interpolate_grad(known, i3, w3, f128))
+    rows.append({"op": "three_interpolate_grad", "B": B, "N": N, "M": 1024, "C": 128, "ms": mine,
+                 "ref_cuda_ms": None, "speedup": None, "algorithmic_GBs": 4.0 * B * (N * 128 + 1024 * 128 + 6 * N) / mine / 1e6,
+                 "note": "CPU-only op in the reference"})
+    att = torch.rand((B, N), device="cuda", generator=g)
+    dense = (torch.rand((B, N, 3), device="cuda", generator=g) * torch.tensor([12.0, 12.0, 1.5], device="cuda")).contiguous()
+    mine = timeit(lambda: dutils.batched_nms(dense, att, 0.5, 0.01, 512))
+    rows.append({"op": "keypoint_nms", "B": B, "N": N, "ms": mine, "ref_cuda_ms": None, "speedup": None,
+                 "clouds_per_s": B / mine * 1e3, "note": "host numpy + sklearn ball tree in the reference (core/utils.py:15-43)"})
     res = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": hbm, "rows": rows,
            "note": "ref_cuda_ms = the reference's unmodified CUDA kernels compiled for sm_100a (oracle/_ref), "
                    "same inputs, same GPU, CUDA events, median of 3-5; three_nn/three_interpolate have no "

@@ -85,12 +85,20 @@ class FlexConvDilate(nn.Module):
         self.se = SEBlock(c) if add_se == "max_pool" else None
         self.concat_conv1d = FeatureConv1d(c + cin, c) if concat else None
 
-    def forward(self, xyz, feat, knn_indices=None, geometry=None):
-        """xyz [B,N,3], feat [B,N,C] -> new_feat [B,N,outdims[-1]]."""
+    def forward(self, xyz, feat, knn_indices=None, geometry=None, cat=None):
+        """xyz [B,N,3], feat [B,N,C] -> new_feat [B,N,outdims[-1]].
+
+        ``cat`` (dilate > 1 with concat only): a [B,N,outdims[-1]+C] buffer whose LAST C columns already hold
+        ``feat`` (written there by the producing 1x1 layer); the up-sampled features are interpolated straight
+        into its first columns, so the channel concat of core/backbones.py:96-99 is never copied."""
         if self.dilate > 1:
             g = geometry or DilateGeometry(xyz, xyz.shape[1] // self.dilate, self.knn)
             pts = g.points_sampled
-            x = ops.group_point(feat, g.kp_indices.unsqueeze(2)).squeeze(2)
+            if cat is not None:
+                cin = cat.shape[2] - self.outdims[-1]
+                x = ops.group_point_cols(cat, self.outdims[-1], cin, g.kp_indices.unsqueeze(2)).squeeze(2)
+            else:
+                x = ops.group_point(feat, g.kp_indices.unsqueeze(2)).squeeze(2)
             nbr = g.knn_indices
         else:
             g, pts, x = None, xyz, feat
@@ -101,6 +109,9 @@ class FlexConvDilate(nn.Module):
         if self.se is not None:
             x = self.se(x, ops.flex_pool(x, nbr))
         if self.upsample and self.dilate > 1:
+            if cat is not None and self.concat_conv1d is not None:
+                ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True, out=cat, out_col=0)
+                return self.concat_conv1d(cat)
             x = ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True)
         if self.concat_conv1d is not None:
             B, N, C = x.shape
@@ -125,14 +136,21 @@ class LocalBackbone(nn.Module):
         self.stage2 = FlexConvDilate(64, [128, 128], dilate=dilate2, knn=knn, concat=True)
         self.local_stage1_shortcut = FeatureConv1d(64, 128)
 
-    def forward(self, points, knn_ind, geometry=None):
+    def forward(self, points, knn_ind, geometry=None, with_desc=False):
+        """-> feat [B,N,128]; with_desc=True: (feat, l2-normalised feat) from one fused pass (model.py:177-181)."""
         nn_8 = knn_ind if knn_ind.shape[2] == 8 else knn_ind[:, :, :8].contiguous()
         f = self.initconv.forward_pm(points, nn_8, bn=self.initconv_bn, act=ACT_RELU)
         f = ops.flex_pool(f, nn_8)
         x1 = self.stage1(points, f, knn_indices=nn_8)
-        x2 = self.before_stage2_conv1d(x1)
-        x2 = self.stage2(points, x2, geometry=geometry)
-        return ops.add(self.local_stage1_shortcut(x1), x2)
+        B, N, _ = x1.shape
+        # stage2's concat buffer: [up-sampled 128 | before_stage2 64]; the 1x1 layer writes its block in place
+        cat = torch.empty((B, N, self.stage2.outdims[-1] + 64), dtype=x1.dtype, device=x1.device)
+        self.before_stage2_conv1d(x1, out=cat, out_col=self.stage2.outdims[-1])
+        x2 = self.stage2(points, None, geometry=geometry, cat=cat)
+        sc = self.local_stage1_shortcut(x1)
+        if with_desc:
+            return ops.add_l2_normalize_rows(sc, x2, 1e-8)
+        return ops.add(sc, x2)
 
 
 class AttentionHead(nn.Module):

@@ -14,6 +14,12 @@ int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t
 // gather.cu
 int group_point_launch(int b, int n, int c, int m, int s, const float* points, const int32_t* idx,
                        float* out, cudaStream_t st);
+int group_point_ld_launch(int b, int n, int c, int m, int s, const float* points, int ldp, const int32_t* idx,
+                          float* out, cudaStream_t st);
+int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                                const float* wsrc, float* out, int ldo, bool from_dist, cudaStream_t st);
+int add_l2norm_rows_launch(const float* a, const float* b, float* sum, float* y, int M, int C, float eps,
+                           cudaStream_t st);
 int flex_pool_pm_launch(const float* feat, const int32_t* nbr, float* out, int32_t* argmax, int B,
                         int N, int K, int D, cudaStream_t st);
 int flex_pool_cm_launch(const float* feat, const int32_t* nbr, float* out, int32_t* argmax, int B,
@@ -389,6 +395,20 @@ int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int B, int N,
                       int32_t* out_cnt, void* workspace, size_t workspace_bytes, void* stream) {
   return keypoint_nms_launch(xyz_pm, attention, B, N, nms_radius, min_response_ratio, max_keypoints, remove_noise,
                              out_idx, out_cnt, workspace, workspace_bytes, S(stream));
+}
+
+int dh3d_group_point_ld(int b, int n, int c, int m, int nsample, const float* points, int ldp, const int32_t* idx,
+                        float* out, void* stream) {
+  return group_point_ld_launch(b, n, c, m, nsample, points, ldp, idx, out, S(stream));
+}
+int dh3d_three_interpolate_ld(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                              const float* weight_or_dist2, int weight_is_dist2, float* out, int ldo, void* stream) {
+  return three_interpolate_ld_launch(b, m, c, n, points, idx, weight_or_dist2, out, ldo, weight_is_dist2 != 0,
+                                     S(stream));
+}
+int dh3d_add_l2_normalize_rows(const float* a, const float* b, float* sum, float* normalized, int M, int C,
+                               float eps, void* stream) {
+  return add_l2norm_rows_launch(a, b, sum, normalized, M, C, eps, S(stream));
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ static inline int ew_blocks(long long work, int threads) {
 template <int VEC>
 __global__ void group_point_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx,
                                    float* __restrict__ out, long long rows, int rows_per_batch,
-                                   int n, int c) {
+                                   int n, int c, int ldp) {
   const int cv = c / VEC;
   const long long total = rows * cv;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -37,26 +37,31 @@ __global__ void group_point_kernel(const float* __restrict__ points, const int32
     const int col = (int)(e - r * cv) * VEC;
     const long long b = r / rows_per_batch;
     const int ii = __ldg(idx + r);
-    const float* src = points + ((long long)b * n + ii) * c + col;
+    const float* src = points + ((long long)b * n + ii) * ldp + col;
     float* dst = out + r * c + col;
     if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = ldg4(src);
     else *dst = __ldg(src);
   }
 }
 
-int group_point_launch(int b, int n, int c, int m, int s, const float* points, const int32_t* idx,
-                       float* out, cudaStream_t st) {
+// ldp = row stride of `points` in floats (>= c): the source may be a column block of a wider tensor
+int group_point_ld_launch(int b, int n, int c, int m, int s, const float* points, int ldp, const int32_t* idx,
+                          float* out, cudaStream_t st) {
   if (!points || !idx || !out) return DH3D_ERR_NULL;
-  if (b <= 0 || n <= 0 || c <= 0 || m <= 0 || s <= 0) return DH3D_ERR_DIM;
+  if (b <= 0 || n <= 0 || c <= 0 || m <= 0 || s <= 0 || ldp < c) return DH3D_ERR_DIM;
   const long long rows = (long long)b * m * s;
-  const bool vec = (c % 4 == 0) && ((((uintptr_t)points | (uintptr_t)out) & 15) == 0);
+  const bool vec = (c % 4 == 0) && (ldp % 4 == 0) && ((((uintptr_t)points | (uintptr_t)out) & 15) == 0);
   if (vec)
     group_point_kernel<4><<<ew_blocks(rows * (c / 4), 256), 256, 0, st>>>(points, idx, out, rows,
-                                                                        m * s, n, c);
+                                                                        m * s, n, c, ldp);
   else
     group_point_kernel<1><<<ew_blocks(rows * c, 256), 256, 0, st>>>(points, idx, out, rows, m * s,
-                                                                  n, c);
+                                                                  n, c, ldp);
   return launch_status();
+}
+int group_point_launch(int b, int n, int c, int m, int s, const float* points, const int32_t* idx,
+                       float* out, cudaStream_t st) {
+  return group_point_ld_launch(b, n, c, m, s, points, c, idx, out, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,7 +336,7 @@ int three_nn_launch(int b, int n, int m, const float* xyz1, const float* xyz2, f
 template <int VEC, bool FROM_DIST>
 __global__ void three_interp_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx,
                                     const float* __restrict__ wsrc, float* __restrict__ out,
-                                    long long rows, int n, int m, int c) {
+                                    long long rows, int n, int m, int c, int ldo) {
   const int cv = c / VEC;
   const long long total = rows * cv;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -358,23 +363,30 @@ __global__ void three_interp_kernel(const float* __restrict__ points, const int3
       o.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(bb.y, w2)), __fmul_rn(cc.y, w3));
       o.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(bb.z, w2)), __fmul_rn(cc.z, w3));
       o.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(bb.w, w2)), __fmul_rn(cc.w, w3));
-      *reinterpret_cast<float4*>(out + r * c + col) = o;
+      *reinterpret_cast<float4*>(out + r * ldo + col) = o;
     } else {
-      out[r * c + col] = __fadd_rn(
+      out[r * ldo + col] = __fadd_rn(
           __fadd_rn(__fmul_rn(__ldg(p1), w1), __fmul_rn(__ldg(p2), w2)), __fmul_rn(__ldg(p3), w3));
     }
   }
 }
 
+// ldo = row stride of `out` in floats (>= c): the result may land in a column block of a wider tensor (fused concat)
+int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                                const float* wsrc, float* out, int ldo, bool from_dist, cudaStream_t st);
 int three_interpolate_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
                              const float* wsrc, float* out, bool from_dist, cudaStream_t st) {
+  return three_interpolate_ld_launch(b, m, c, n, points, idx, wsrc, out, c, from_dist, st);
+}
+int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                                const float* wsrc, float* out, int ldo, bool from_dist, cudaStream_t st) {
   if (!points || !idx || !wsrc || !out) return DH3D_ERR_NULL;
-  if (b <= 0 || m <= 0 || c <= 0 || n <= 0) return DH3D_ERR_DIM;
+  if (b <= 0 || m <= 0 || c <= 0 || n <= 0 || ldo < c) return DH3D_ERR_DIM;
   const long long rows = (long long)b * n;
-  const bool vec = (c % 4 == 0) && ((((uintptr_t)points | (uintptr_t)out) & 15) == 0);
+  const bool vec = (c % 4 == 0) && (ldo % 4 == 0) && ((((uintptr_t)points | (uintptr_t)out) & 15) == 0);
 #define DH3D_TI(V, FD)                                                                          \
   three_interp_kernel<V, FD><<<ew_blocks(rows * (c / V), 256), 256, 0, st>>>(points, idx, wsrc, out, \
-                                                                            rows, n, m, c)
+                                                                            rows, n, m, c, ldo)
   if (vec) { if (from_dist) DH3D_TI(4, true); else DH3D_TI(4, false); }
   else { if (from_dist) DH3D_TI(1, true); else DH3D_TI(1, false); }
 #undef DH3D_TI
@@ -685,6 +697,43 @@ int l2norm_rows_launch(const float* x, int ldx, float* y, int ldy, int M, int C,
   if (M <= 0 || C <= 0 || C % 4 || ldx % 4 || ldy % 4) return DH3D_ERR_DIM;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return DH3D_ERR_ALIGN;
   l2norm_rows_kernel<<<ew_blocks((long long)M * 32, 256), 256, 0, st>>>(x, ldx, y, ldy, M, C, eps);
+  return launch_status();
+}
+
+// one warp per row: s = a + b;  y = s / sqrt(max(sum s^2, eps)).  Both results are written (the raw sum feeds the
+// detector / global branch, the normalised rows are the local descriptors): one pass instead of add + l2norm.
+__global__ void add_l2norm_rows_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                       float* __restrict__ sum, float* __restrict__ y, long long M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < M; r += nwarps) {
+    const float* ar = a + r * C;
+    const float* br = b + r * C;
+    float4 v[4];  // C <= 512
+    float ss = 0.f;
+    int i = 0;
+    for (int c = lane * 4; c < C; c += 128, ++i) {
+      const float4 x = ldg4(ar + c), z = ldg4(br + c);
+      v[i] = make_float4(x.x + z.x, x.y + z.y, x.z + z.z, x.w + z.w);
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+      *reinterpret_cast<float4*>(sum + r * C + c) = v[i];
+    }
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(fmaxf(ss, eps));
+    i = 0;
+    for (int c = lane * 4; c < C; c += 128, ++i)
+      *reinterpret_cast<float4*>(y + r * C + c) = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+  }
+}
+
+int add_l2norm_rows_launch(const float* a, const float* b, float* sum, float* y, int M, int C, float eps,
+                           cudaStream_t st) {
+  if (!a || !b || !sum || !y) return DH3D_ERR_NULL;
+  if (M <= 0 || C <= 0 || C % 4) return DH3D_ERR_DIM;
+  if (C > 512) return DH3D_ERR_UNSUPPORTED;
+  if ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)sum | (uintptr_t)y) & 15) != 0) return DH3D_ERR_ALIGN;
+  add_l2norm_rows_kernel<<<ew_blocks((long long)M * 32, 256), 256, 0, st>>>(a, b, sum, y, M, C, eps);
   return launch_status();
 }
 

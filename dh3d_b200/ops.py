@@ -170,14 +170,41 @@ def three_nn(xyz1, xyz2, exhaustive=False):
     return dist, idx
 
 
-def three_interpolate(points, idx, weight, weight_is_dist2=False):
+def three_interpolate(points, idx, weight, weight_is_dist2=False, out=None, out_col=0):
+    """``out``/``out_col``: write into columns [out_col, out_col+c) of an existing [B,n,ld] tensor (fused concat)."""
     B, m, c = points.shape
     n = idx.shape[1]
+    if out is not None:
+        check(out, f32, "out", 3)
+        call("dh3d_three_interpolate_ld", B, m, c, n, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
+             check(weight, f32, "weight", 3), int(bool(weight_is_dist2)),
+             ctypes.c_void_p(out.data_ptr() + 4 * out_col), out.shape[-1], stream_ptr(points.device))
+        return out
     out = torch.empty((B, n, c), dtype=f32, device=points.device)
     name = "dh3d_three_interpolate_from_dist" if weight_is_dist2 else "dh3d_three_interpolate"
     call(name, B, m, c, n, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
          check(weight, f32, "weight", 3), check(out, f32, "out"), stream_ptr(points.device))
     return out
+
+
+def group_point_cols(wide, col, c, idx):
+    """group_point on the column block [col, col+c) of ``wide`` [B,N,ld]: -> [B,M,S,c]."""
+    B, N, ld = wide.shape
+    _, M, S = idx.shape
+    out = torch.empty((B, M, S, c), dtype=f32, device=wide.device)
+    check(wide, f32, "wide", 3)
+    call("dh3d_group_point_ld", B, N, c, M, S, ctypes.c_void_p(wide.data_ptr() + 4 * col), ld,
+         check(idx, i32, "idx", 3), check(out, f32, "out"), stream_ptr(wide.device))
+    return out
+
+
+def add_l2_normalize_rows(a, b, eps):
+    """(a + b, l2-normalised rows of a + b) in one pass."""
+    M, C = _rows(a)
+    s, y = torch.empty_like(a), torch.empty_like(a)
+    call("dh3d_add_l2_normalize_rows", check(a, f32, "a"), check(b, f32, "b"), check(s, f32, "sum"),
+         check(y, f32, "y"), M, C, _cf(float(eps)), stream_ptr(a.device))
+    return s, y
 
 
 def _rows(x):

@@ -296,6 +296,23 @@ DH3D_API int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int 
                       float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
                       int32_t* out_cnt, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Strided / fused variants used by the forward pass to avoid materialising the channel concat of
+ * flex_conv_dilate (core/backbones.py:96-99) and the separate add + l2-normalise (backbone_local_dilate
+ * :127 + model.py:177-181).  Results are bit-identical to the unfused sequence.
+ *   dh3d_group_point_ld: `points` rows have stride ldp >= c floats (a column block of a wider tensor).
+ *   dh3d_three_interpolate_ld: `out` rows have stride ldo >= c floats; weight_is_dist2 != 0 derives the
+ *     inverse-distance weights from the squared distances in-kernel (backbones.py:92-95).
+ *   dh3d_add_l2_normalize_rows: sum = a + b and normalized = sum / sqrt(max(|sum|^2, eps)), [M,C] each.
+ * ------------------------------------------------------------------------------------------- */
+DH3D_API int dh3d_group_point_ld(int b, int n, int c, int m, int nsample, const float* points, int ldp,
+                        const int32_t* idx, float* out, void* stream);
+DH3D_API int dh3d_three_interpolate_ld(int b, int m, int c, int n, const float* points, const int32_t* idx,
+                              const float* weight_or_dist2, int weight_is_dist2, float* out, int ldo,
+                              void* stream);
+DH3D_API int dh3d_add_l2_normalize_rows(const float* a, const float* b, float* sum, float* normalized, int M, int C,
+                               float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -405,3 +405,26 @@ def test_netvlad_tiny_and_huge_feature_norms():
     att = rng.rand(2, 1000, 1).astype(np.float32)
     out = blk(None, cu(feat), cu(att), final_l2norm=True)
     close(out, net.netvlad(feat, att, p, final_l2norm=True))
+
+
+# ------------------------------------------------------------------------ fused concat / add+l2norm
+def test_strided_group_interp_and_add_l2norm_are_bit_identical_to_the_unfused_ops():
+    from dh3d_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, N, M = 2, 3000, 256
+    wide = torch.randn((B, N, 192), device="cuda", generator=g)
+    idx = torch.randint(0, N, (B, M, 1), device="cuda", generator=g, dtype=torch.int32)
+    a = ops.group_point_cols(wide, 128, 64, idx)
+    b = ops.group_point(wide[:, :, 128:].contiguous(), idx)
+    assert torch.equal(a, b)
+    known = torch.randn((B, M, 128), device="cuda", generator=g)
+    i3 = torch.randint(0, M, (B, N, 3), device="cuda", generator=g, dtype=torch.int32)
+    d3 = torch.rand((B, N, 3), device="cuda", generator=g)
+    before = wide.clone()
+    ops.three_interpolate(known, i3, d3, weight_is_dist2=True, out=wide, out_col=0)
+    assert torch.equal(wide[:, :, :128], ops.three_interpolate(known, i3, d3, weight_is_dist2=True))
+    assert torch.equal(wide[:, :, 128:], before[:, :, 128:])          # the other column block is untouched
+    x, y = torch.randn((B, N, 128), device="cuda", generator=g), torch.randn((B, N, 128), device="cuda", generator=g)
+    s, nrm = ops.add_l2_normalize_rows(x, y, 1e-8)
+    assert torch.equal(s, ops.add(x, y))
+    assert torch.equal(nrm, ops.l2_normalize_rows(ops.add(x, y), 1e-8))

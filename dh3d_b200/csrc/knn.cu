@@ -3,9 +3,10 @@
 //
 // The reference launches one CTA per QUERY point and radix-sorts all N keys to extract K of them
 // (N <= 8192, followed by a device sync).  Here:
-//   1. knn_sort_kernel (one CTA per cloud): counting sort of the points by the Morton code of a
+//   1. knn_sort_kernel (one CTA per cloud): counting sort of the points by the Hilbert index of a
 //      16^3 grid cell -> spatially coherent float4 array (x,y,z,original index) + one bounding box
-//      per 64-point chunk.
+//      per 32-point chunk + one per 16 chunks (two-level: a warp tests 16 coarse boxes, then only the fine
+//      boxes inside the coarse ones that can still matter).
 //   2. knn_query_kernel: one thread per query (queries taken in sorted order, so a warp's 32 queries
 //      are neighbours) with a sorted top-K list in registers.  Each warp walks the chunks outward from
 //      its own; a chunk is skipped when, for every lane, a lower bound of the distance to the chunk's
@@ -33,7 +34,8 @@ size_t knn_tiled_workspace_bytes(int B, int N);
 int knn_tiled_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
                      float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-constexpr int kKnnChunk = 64;       // candidates per bounding box
+constexpr int kKnnChunk = 32;       // candidates per bounding box (one per lane of the box-building warp)
+constexpr int kKnnSuper = 16;       // chunks per second-level box (512 points)
 constexpr int kKnnThreads = 128;    // queries per CTA
 constexpr int kSortThreads = 1024;
 constexpr int kCells = 4096;        // 16^3 Morton-ordered grid cells
@@ -68,6 +70,10 @@ __device__ __forceinline__ int knn_point_of(int r, int T, int logV) {
 }
 
 static inline int knn_padded(int N) { return ceil_div(N, kKnnChunk) * kKnnChunk; }
+// float4s of box storage per cloud: (min,max) per chunk, then (min,max) per super-chunk
+static inline size_t knn_box_f4(int Np) {
+  return 2 * (size_t)(Np / kKnnChunk) + 2 * (size_t)ceil_div(Np / kKnnChunk, kKnnSuper);
+}
 
 static bool knn_use_tiled() {
   static const bool t = [] {
@@ -80,9 +86,14 @@ static bool knn_use_tiled() {
 size_t knn_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
   const size_t np = knn_padded(N);
-  const size_t pruned = (size_t)B * (np * sizeof(float4) + (np / kKnnChunk) * 2 * sizeof(float4));
+  const size_t pruned = (size_t)B * (np + knn_box_f4((int)np)) * sizeof(float4);
   const size_t tiled = knn_tiled_workspace_bytes(B, N);
   return pruned > tiled ? pruned : tiled;
+}
+
+__device__ __forceinline__ long long knn_box_f4_dev(int Np) {
+  const int nc = Np / kKnnChunk;
+  return 2LL * nc + 2LL * ((nc + kKnnSuper - 1) / kKnnSuper);
 }
 
 __device__ __forceinline__ unsigned spread3(unsigned v) {  // 4 bits -> every third bit
@@ -102,7 +113,7 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = pos + (long long)b * sb;
   float4* out = sorted + (long long)b * Np;
-  float4* bx = boxes + (long long)b * (Np / kKnnChunk) * 2;
+  float4* bx = boxes + (long long)b * knn_box_f4_dev(Np);
 
   // (1) cloud bounding box
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
@@ -154,7 +165,27 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
       int q = (v >= 0.f) ? ((v < 15.f) ? (int)v : 15) : 0;  // NaN -> 0; only the scan order depends on it
       c[d] = (unsigned)q;
     }
-    return (int)(spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2));
+    // Hilbert index of the cell (Skilling's axes-to-transpose, 4 bits per axis): consecutive cells are always
+    // face neighbours, so a window of consecutive sorted points has a compact bounding box (a Morton window
+    // that straddles a block boundary spans far more space: ~80 chunks per warp had to be scanned, ncu r1l)
+    constexpr unsigned Mb = 8u;  // 1 << (bits - 1)
+#pragma unroll
+    for (unsigned Q = Mb; Q > 1u; Q >>= 1) {
+      const unsigned Pm = Q - 1u;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        if (c[d] & Q) c[0] ^= Pm;
+        else { const unsigned t = (c[0] ^ c[d]) & Pm; c[0] ^= t; c[d] ^= t; }
+      }
+    }
+    c[1] ^= c[0];
+    c[2] ^= c[1];
+    unsigned t = 0u;
+#pragma unroll
+    for (unsigned Q = Mb; Q > 1u; Q >>= 1)
+      if (c[2] & Q) t ^= Q - 1u;
+    c[0] ^= t; c[1] ^= t; c[2] ^= t;
+    return (int)(spread3(c[2]) | (spread3(c[1]) << 1) | (spread3(c[0]) << 2));
   };
 
   // (2) histogram, (3) exclusive scan, (4) scatter
@@ -198,18 +229,16 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
     out[i] = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(-1));
   __syncthreads();
 
-  // (5) one bounding box per chunk of 64 sorted points (2 per lane)
-  for (int c = warp; c < Np / kKnnChunk; c += kSortThreads / 32) {
+  // (5) one bounding box per chunk of 32 sorted points (one per lane), (6) one per 16 chunks
+  const int nchunks = Np / kKnnChunk;
+  for (int c = warp; c < nchunks; c += kSortThreads / 32) {
     float bmn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
     float bmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 q = out[c * kKnnChunk + h * 32 + lane];
-      if (__float_as_int(q.w) >= 0) {
-        bmn[0] = fminf(bmn[0], q.x); bmx[0] = fmaxf(bmx[0], q.x);
-        bmn[1] = fminf(bmn[1], q.y); bmx[1] = fmaxf(bmx[1], q.y);
-        bmn[2] = fminf(bmn[2], q.z); bmx[2] = fmaxf(bmx[2], q.z);
-      }
+    const float4 q = out[c * kKnnChunk + lane];
+    if (__float_as_int(q.w) >= 0) {
+      bmn[0] = q.x; bmx[0] = q.x;
+      bmn[1] = q.y; bmx[1] = q.y;
+      bmn[2] = q.z; bmx[2] = q.z;
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d)
@@ -221,6 +250,27 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
     if (lane == 0) {
       bx[2 * c] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
       bx[2 * c + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+    }
+  }
+  __syncthreads();
+  const int nsuper = (nchunks + kKnnSuper - 1) / kKnnSuper;
+  float4* sbx = bx + 2 * nchunks;
+  for (int s = warp; s < nsuper; s += kSortThreads / 32) {
+    const int c = s * kKnnSuper + (lane & (kKnnSuper - 1));
+    float4 lo4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+    float4 hi4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
+    if (c < nchunks) { lo4 = bx[2 * c]; hi4 = bx[2 * c + 1]; }
+    float bmn[3] = {lo4.x, lo4.y, lo4.z}, bmx[3] = {hi4.x, hi4.y, hi4.z};
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        bmn[d] = fminf(bmn[d], __shfl_xor_sync(0xffffffffu, bmn[d], o));
+        bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o));
+      }
+    if (lane == 0) {
+      sbx[2 * s] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
+      sbx[2 * s + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
     }
   }
 }
@@ -272,12 +322,15 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
                  const float4* __restrict__ boxes, int Np, int T, int logT, int logV, int K, int flush_min,
                  int32_t* __restrict__ ids, float* __restrict__ dists) {
   __shared__ float2 s_buf[kKnnCap][kKnnThreads];
+  __shared__ __align__(16) float4 s_chunk[kKnnThreads / 32][kKnnChunk];
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int p = blockIdx.x * kKnnThreads + tid;  // sorted position of this thread's query
   const float4* cloud = sorted + (long long)b * Np;
-  const float4* bx = boxes + (long long)b * (Np / kKnnChunk) * 2;
+  const float4* bx = boxes + (long long)b * knn_box_f4_dev(Np);
   const int nchunks = Np / kKnnChunk;
+  const int nsuper = (nchunks + kKnnSuper - 1) / kKnnSuper;
+  const float4* sbx = bx + 2 * nchunks;
 
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int y = -1;
@@ -334,8 +387,8 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
     if (active) thr2 = M::bound(__uint_as_float((uint32_t)(kth >> 32)));
   };
 
-  auto box_lb = [&](int c) -> float {
-    const float4 lo4 = __ldg(bx + 2 * c), hi4 = __ldg(bx + 2 * c + 1);
+  auto box_lb = [&](const float4* boxp, int c) -> float {
+    const float4 lo4 = __ldg(boxp + 2 * c), hi4 = __ldg(boxp + 2 * c + 1);
     // lower bound of the computed d2 to any point in the box (same op sequence, monotone roundings)
     const float ex = fmaxf(fmaxf(lo4.x - qx, qx - hi4.x), 0.f);
     const float ey = fmaxf(fmaxf(lo4.y - qy, qy - hi4.y), 0.f);
@@ -350,7 +403,7 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
     float best = CUDART_INF_F;
     int bc = 0;
     for (int c = 0; c < nchunks; ++c) {
-      const float lb = box_lb(c);
+      const float lb = box_lb(bx, c);
       if (lb < best) { best = lb; bc = c; }
     }
     // the warp's first active lane decides (queries of a warp are spatial neighbours)
@@ -358,26 +411,86 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
     c0 = __shfl_sync(0xffffffffu, bc, act ? __ffs(act) - 1 : 0);
   }
 
-  // walk outward: c0, c0+1, c0-1, c0+2, ...
-  const int reach = max(c0, nchunks - 1 - c0);
-  for (int step = 0; step <= 2 * reach; ++step) {
-    const int c = (step & 1) ? c0 + ((step + 1) >> 1) : c0 - (step >> 1);
-    if (c < 0 || c >= nchunks) continue;
-    if (!__any_sync(0xffffffffu, box_lb(c) <= thr2)) continue;
-    const float4* cand = cloud + c * kKnnChunk;
-    for (int j0 = 0; j0 < kKnnChunk; j0 += 8) {
+  // bounding box of the warp's 32 queries (for the lane-parallel coarse test of 16 fine boxes at once)
+  float wlo[3] = {active ? qx : CUDART_INF_F, active ? qy : CUDART_INF_F, active ? qz : CUDART_INF_F};
+  float whi[3] = {active ? qx : -CUDART_INF_F, active ? qy : -CUDART_INF_F, active ? qz : -CUDART_INF_F};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 v = __ldg(cand + j0 + u);
-        const float d2 = M::d2(v.x - qx, v.y - qy, v.z - qz);
-        if (d2 <= thr2) {
-          s_buf[cnt][tid] = make_float2(d2, v.w);
-          ++cnt;
-        }
-      }
-      if (__any_sync(0xffffffffu, cnt > kKnnCap - 8)) flush();
+  for (int d = 0; d < 3; ++d)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wlo[d] = fminf(wlo[d], __shfl_xor_sync(0xffffffffu, wlo[d], o));
+      whi[d] = fmaxf(whi[d], __shfl_xor_sync(0xffffffffu, whi[d], o));
     }
-    if (__any_sync(0xffffffffu, cnt >= flush_min)) flush();
+  const int lane = tid & 31;
+
+  // two-level walk: super-chunks outward from the warp's own (s0, s0+1, s0-1, ...).  Inside a surviving
+  // super-chunk lane j loads fine box j ONCE (one coalesced request instead of 16 dependent uniform loads) and
+  // bounds the distance between it and the warp's query box; a chunk is then visited only if that coarse bound
+  // is within the largest per-lane bound, and scanned only if the exact per-lane test (box broadcast by shuffles)
+  // passes.  Chunks nearest (in sorted order) to the warp's own chunk come first, so the bounds tighten early.
+  const int s0 = c0 / kKnnSuper;
+  const int sreach = max(s0, nsuper - 1 - s0);
+  for (int sstep = 0; sstep <= 2 * sreach; ++sstep) {
+    const int sc = (sstep & 1) ? s0 + ((sstep + 1) >> 1) : s0 - (sstep >> 1);
+    if (sc < 0 || sc >= nsuper) continue;
+    if (!__any_sync(0xffffffffu, box_lb(sbx, sc) <= thr2)) continue;
+    const int cbeg = sc * kKnnSuper, cend = min(cbeg + kKnnSuper, nchunks);
+    const int cn = cend - cbeg;
+    float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
+    float lbw = CUDART_INF_F;
+    {
+      const int j = lane & (kKnnSuper - 1);
+      if (j < cn) {
+        blo = __ldg(bx + 2 * (cbeg + j));
+        bhi = __ldg(bx + 2 * (cbeg + j) + 1);
+        // p in [blo,bhi], q in [wlo,whi]: fl(p - q) >= fl(blo - whi) and fl(q - p) >= fl(wlo - bhi) (monotone rounding)
+        const float ex = fmaxf(fmaxf(blo.x - whi[0], wlo[0] - bhi.x), 0.f);
+        const float ey = fmaxf(fmaxf(blo.y - whi[1], wlo[1] - bhi.y), 0.f);
+        const float ez = fmaxf(fmaxf(blo.z - whi[2], wlo[2] - bhi.z), 0.f);
+        lbw = M::d2(ex, ey, ez);
+      }
+    }
+    // start inside this super-chunk: own chunk, or the end facing the own super-chunk
+    const int cs = (sc == s0) ? c0 : (sc > s0 ? cbeg : cend - 1);
+    for (int step = 0; step < 2 * cn; ++step) {
+      const int c = (step & 1) ? cs + ((step + 1) >> 1) : cs - (step >> 1);
+      if (c < cbeg || c >= cend) continue;
+      const int j = c - cbeg;
+      // largest bound in the warp (non-negative floats order like their bit patterns; inactive lanes hold -1)
+      const float tmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(thr2)));
+      if (!(__shfl_sync(0xffffffffu, lbw, j) <= tmax)) continue;
+      {
+        const float lx = __shfl_sync(0xffffffffu, blo.x, j), ly = __shfl_sync(0xffffffffu, blo.y, j),
+                    lz = __shfl_sync(0xffffffffu, blo.z, j);
+        const float hx = __shfl_sync(0xffffffffu, bhi.x, j), hy = __shfl_sync(0xffffffffu, bhi.y, j),
+                    hz = __shfl_sync(0xffffffffu, bhi.z, j);
+        const float ex = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
+        const float ey = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
+        const float ez = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
+        if (!__any_sync(0xffffffffu, M::d2(ex, ey, ez) <= thr2)) continue;
+      }
+      // one coalesced 512-byte load per chunk, staged in the warp's shared-memory slot and read back as LDS.128
+      // broadcasts
+      const float4 mine = __ldg(cloud + c * kKnnChunk + lane);
+      __syncwarp();
+      s_chunk[tid >> 5][lane] = mine;
+      __syncwarp();
+      const float4* cand = s_chunk[tid >> 5];
+#pragma unroll
+      for (int j0 = 0; j0 < kKnnChunk; j0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 v = cand[j0 + u];
+          const float d2 = M::d2(v.x - qx, v.y - qy, v.z - qz);
+          if (d2 <= thr2) {
+            s_buf[cnt][tid] = make_float2(d2, v.w);
+            ++cnt;
+          }
+        }
+        if (__any_sync(0xffffffffu, cnt > kKnnCap - 8)) flush();
+      }
+      if (__any_sync(0xffffffffu, cnt >= flush_min)) flush();
+    }
   }
   flush();
 
@@ -459,7 +572,7 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
 size_t three_nn_workspace_bytes(int b, int n, int m) {
   if (b <= 0 || n <= 0 || m <= 0) return 0;
   const size_t np1 = knn_padded(n), np2 = knn_padded(m);
-  return (size_t)b * (np2 + 2 * (np2 / kKnnChunk) + np1 + 2 * (np1 / kKnnChunk)) * sizeof(float4);
+  return (size_t)b * (np2 + knn_box_f4(np2) + np1 + knn_box_f4(np1)) * sizeof(float4);
 }
 
 int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
@@ -472,7 +585,7 @@ int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* 
   const int np1 = knn_padded(n), np2 = knn_padded(m);
   float4* cands = reinterpret_cast<float4*>(workspace);
   float4* boxes = cands + (size_t)b * np2;
-  float4* queries = boxes + (size_t)b * 2 * (np2 / kKnnChunk);
+  float4* queries = boxes + (size_t)b * knn_box_f4(np2);
   float4* qboxes = queries + (size_t)b * np1;
   knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, queries, qboxes);
   int rc = launch_status();

@@ -18,6 +18,8 @@ One structural difference from the reference graph: FPS, the k-NN of the sampled
 use dilate 8 on the same xyz, so they are computed ONCE per cloud (``DilateGeometry``) and shared
 (the reference recomputes them).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -70,6 +72,16 @@ class SEBlock(nn.Module):
     def forward(self, x, pooled):
         return ops.se_excite(x, self.f2(self.f1(pooled)))
 
+    def forward_fused(self, x, nbr):
+        """flex_pool + both 1x1 layers + excite in one launch (``dh3d_se_pool_excite``); None when the
+        shape is not one the fused kernel covers (the caller then composes the separate ops)."""
+        C = x.shape[2]
+        if C not in (64, 128) or os.environ.get("DH3D_SE", "fused").lower().startswith("s"):
+            return None
+        w1, _, b1, _ = self.f1.tfconv0.folded()
+        w2, _, b2, _ = self.f2.tfconv0.folded()
+        return ops.se_pool_excite(x, nbr, w1, b1, w2, b2)
+
 
 class FlexConvDilate(nn.Module):
     def __init__(self, cin, outdims, dilate, knn=8, concat=True, add_se="max_pool", upsample=True):
@@ -107,7 +119,8 @@ class FlexConvDilate(nn.Module):
             x = getattr(self, "flexconv_%d" % i).forward_pm(
                 x, pts, nbr, bn=getattr(self, "flexconv_%d_bn" % i), act=ACT_RELU)
         if self.se is not None:
-            x = self.se(x, ops.flex_pool(x, nbr))
+            y = self.se.forward_fused(x, nbr)
+            x = y if y is not None else self.se(x, ops.flex_pool(x, nbr))
         if self.upsample and self.dilate > 1:
             if cat is not None and self.concat_conv1d is not None:
                 ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True, out=cat, out_col=0)

@@ -43,6 +43,9 @@ int query_ball_launch(int b, int n, int m, float radius, int nsample, const floa
                       cudaStream_t st);
 int transpose_launch(const void* src, void* dst, int B, int R, int C, cudaStream_t st);
 int se_excite_launch(const float* x, const float* g, float* y, size_t count, cudaStream_t st);
+// se_fused.cu
+int se_pool_excite_launch(const float* x, const int32_t* nbr, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* out, int B, int N, int K, int C, int H, cudaStream_t st);
 int add_launch(const float* a, const float* b, float* y, size_t count, cudaStream_t st);
 int copy_cols_launch(const float* src, int lds, float* dst, int ldd, int M, int C, cudaStream_t st);
 int l2norm_rows_launch(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
@@ -294,6 +297,11 @@ int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, fl
 }
 int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream) {
   return se_excite_launch(x, gate, y, count, S(stream));
+}
+int dh3d_se_pool_excite(const float* x, const int32_t* neighborhood, const float* w1, const float* b1,
+                        const float* w2, const float* b2, float* y, int B, int N, int K, int C, int H,
+                        void* stream) {
+  return se_pool_excite_launch(x, neighborhood, w1, b1, w2, b2, y, B, N, K, C, H, S(stream));
 }
 int dh3d_l2_normalize_rows(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
                            void* stream) {

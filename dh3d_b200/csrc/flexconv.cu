@@ -193,7 +193,8 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
   if (tc && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) {
     // measured (B200, r1h): cp.async staging wins for Din >= 64 (0.2125 vs 0.2216 ms at 64->64 x 262144 points,
     // 0.111 vs 0.130 ms at 128->256 x 32768), the per-thread gather for Din = 32 (0.122 vs 0.139 ms)
-    if (flexconv_mode() == 0 && Din >= 64)
+    static const int ca_min_din = getenv("DH3D_FLEXCONV_CA_MIN_DIN") ? atoi(getenv("DH3D_FLEXCONV_CA_MIN_DIN")) : 64;
+    if (flexconv_mode() == 0 && Din >= ca_min_din)
       return flexconv_ca_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
                                 Dout, st);
     if (flexconv_mode() == 3)

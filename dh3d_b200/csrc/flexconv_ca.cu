@@ -33,19 +33,38 @@ constexpr int kCAConsumerWarps = 16;
 constexpr int kCAKB = 8;                        // neighbour slots per offset-table batch
 constexpr uint32_t kCAStageBytes = 128 * 128;   // 128 rows x 32 channels fp32
 
-template <int BN>
+// K8 = the K == 8 fast path (every FlexConv of DH3D): the neighbour loop is fully unrolled, so the ring slot, the
+// table slot and the operand stage of every item are compile-time constants and the issue cursor advances at one
+// static point per group (see the consumer branch).
+template <int BN, bool K8>
 struct CACfg {
   static constexpr int kStages = 2;                           // UMMA operand stages
-  static constexpr int kGStages = BN <= 64 ? 5 : 3;           // gather stages (16 KB each)
+  static constexpr int kGStages = K8 ? 4 : (BN <= 64 ? 5 : 3);   // gather stages (16 KB each)
+  static constexpr int kOutRows = (K8 && BN > 64) ? 16 : 32;  // rows per epilogue TMA store (smem budget)
+  static constexpr uint32_t kOutBytes = 4 * kOutRows * 32 * 4;
   static constexpr uint32_t kBBytes = BN * kTcBK * 4;
   static constexpr uint32_t kStageBytes = 2 * kTcABytes + 2 * kBBytes;
   static constexpr uint32_t kDeltaBytes = 128 * kCAKB * 16;   // float4 per (row, slot)
   static constexpr uint32_t kIdxBytes = 128 * kCAKB * 4;      // global feature row per (row, slot)
   static constexpr uint32_t kParamBytes = 2 * 2 * BN * 4;     // double-buffered scale/shift slices
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kGStages * kCAStageBytes + kDeltaBytes +
-                                         kIdxBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+                                         kIdxBytes + kOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
+
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work; same IEEE results)
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long f, float s) {
+  asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nfma.rn.f32x2 %0, %1, t, %0;\n}" : "+l"(acc) : "l"(f), "f"(s));
+}
+__device__ __forceinline__ void fadd2(unsigned long long& acc, unsigned long long f) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(f));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
 
 struct CAArgs {
   const float* feat;     // [rows, Din]
@@ -61,12 +80,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-template <int BN>
+template <int BN, bool K8>
 __global__ void __launch_bounds__(kCAThreads, 1)
 flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY,
                    const CAArgs a) {
-  using Cfg = CACfg<BN>;
+  using Cfg = CACfg<BN, K8>;
   constexpr int S = Cfg::kStages;
   constexpr int G = Cfg::kGStages;
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +94,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
   float4* sdelta = reinterpret_cast<float4*>(gbase + G * kCAStageBytes);   // [128][kCAKB]
   int* sidx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sdelta) + Cfg::kDeltaBytes);  // [128][kCAKB]
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(sidx) + Cfg::kIdxBytes;
-  float* params = reinterpret_cast<float*>(out_stage + kTcStageOutBytes);  // [2][2][BN]
+  float* params = reinterpret_cast<float*>(out_stage + Cfg::kOutBytes);  // [2][2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);
   uint64_t* bfull = bars;               // [S] Theta tiles landed          (count 1 + tx)
   uint64_t* afull = bars + S;           // [S] A hi/lo slab written        (count 16, one per consumer warp)
@@ -172,7 +191,125 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
         }
     }
   } else if (warp < 18) {
-    // ------------------------------------------------------------------ consumers (16 warps x 8 rows)
+   if constexpr (K8) {
+    // ------------------------------------------------------------------ consumers, K == 8 (16 warps x 8 rows)
+    // lane = (row-in-warp rw = lane & 7, channel segment seg = lane >> 3): a quarter-warp is 8 rows x one
+    // 16-byte chunk, so with the 128B-swizzle chunk index (chunk ^ rw) every LDS.128 / STS.128 below -- gather
+    // ring, A slabs, offset table -- touches 8 distinct 16-byte columns: no bank conflicts (the (row, seg)
+    // mapping of the generic path had 2-way conflicts on all three; ncu r1j: 10.8 M of 26 M wavefronts).
+    // Item i of a group is neighbour slot k = i; the ring slot is k & 3, the item issued while item k is
+    // being reduced is k + 3 (next group when k >= 5), all static under the unroll.
+    constexpr int AH = G - 1;     // items in flight per thread
+    static_assert(G == 4, "the unrolled K == 8 schedule assumes a 4-slot ring");
+    const int wc = warp - 2;
+    const int rw = lane & 7, seg = lane >> 3;
+    const int r = 8 * wc + rw;
+    const uint32_t o0 = r * 128 + ((seg ^ rw) << 4), o1 = r * 128 + (((seg + 4) ^ rw) << 4);
+    float4* drow = sdelta + r * kCAKB;   // slot k at drow[k ^ rw]
+    int* irow = sidx + r * kCAKB;        // slot k at irow[k ^ rw]
+    const int groups = num_nt * num_cg;
+
+    // ---- issue side: tile i_mt, group (i_nt, i_cg); entering a tile fills the index table of this warp's rows
+    // and starts the loads the offset table of that tile will need three items later
+    int i_mt = blockIdx.x, i_cg = 0, i_g = 0;
+    float nx[6], pc[3];
+    auto enter_tile = [&](int mt) {
+      const int row = mt * kTcBM + r;
+      const int rr = row < a.rows ? row : 0;   // tail rows gather row 0 (their outputs are clipped)
+      const int cloud0 = (rr / a.n_per_cloud) * a.n_per_cloud;
+      const int2 nb = __ldg(reinterpret_cast<const int2*>(a.nbr + (long long)rr * 8 + 2 * seg));
+      const int v0 = cloud0 + nb.x, v1 = cloud0 + nb.y;
+      __syncwarp();
+      irow[(2 * seg) ^ rw] = v0;
+      irow[(2 * seg + 1) ^ rw] = v1;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        nx[c] = __ldg(a.xyz + (long long)v0 * 3 + c);
+        nx[3 + c] = __ldg(a.xyz + (long long)v1 * 3 + c);
+        pc[c] = __ldg(a.xyz + (long long)rr * 3 + c);
+      }
+    };
+    auto issue = [&](int k, int slot) {
+      if (i_mt < num_mt) {
+        const float* src = a.feat + (long long)irow[k ^ rw] * a.Din + i_cg * kTcBK + seg * 4;
+        uint8_t* dst = gbase + slot * kCAStageBytes;
+        cp_async16(dst + o0, src);
+        cp_async16(dst + o1, src + 16);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");  // one group per item, empty past the end
+    };
+    auto next_group = [&]() {
+      if (++i_cg == num_cg) i_cg = 0;
+      if (++i_g == groups) {
+        i_g = 0;
+        i_mt += gridDim.x;
+        if (i_mt < num_mt) enter_tile(i_mt);
+      }
+    };
+    if (i_mt < num_mt) enter_tile(i_mt);
+#pragma unroll
+    for (int i = 0; i < AH; ++i) issue(i, i);
+
+    // ---- consume side
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
+      // offset table of this tile from the coordinates loaded when the issue side entered it
+      __syncwarp();
+      drow[(2 * seg) ^ rw] = make_float4(nx[0] - pc[0], nx[1] - pc[1], nx[2] - pc[2], 0.f);
+      drow[(2 * seg + 1) ^ rw] = make_float4(nx[3] - pc[0], nx[4] - pc[1], nx[5] - pc[2], 0.f);
+      __syncwarp();
+      for (int g = 0; g < groups; ++g) {
+        unsigned long long m[4][4];  // [moment p'][channel pair]
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m[p][c] = 0ull;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(AH - 1) : "memory");  // this thread's item k landed
+          const uint8_t* gs = gbase + (k & 3) * kCAStageBytes;
+          const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(gs + o0);
+          const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(gs + o1);
+          const float4 d = drow[k ^ rw];
+          const unsigned long long fv[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            fadd2(m[0][c], fv[c]);
+            ffma2(m[1][c], fv[c], d.x);
+            ffma2(m[2][c], fv[c], d.y);
+            ffma2(m[3][c], fv[c], d.z);
+          }
+          if (k == 8 - AH) next_group();
+          issue((k + AH) & 7, (k + AH) & 3);
+        }
+        // 4 K-slabs (p' = 1, x, y, z) -> operand stages p' & 1, swizzled K-major, hi (raw) + lo
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int s = p & 1;
+          mbar_wait(&empty[s], (uint32_t)(p >> 1) ^ 1u);   // slab counter 4g + p: parity (p >> 1) for S == 2
+          uint8_t* ah = stage_a(s);
+          uint8_t* al = stage_alo(s);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t off = j ? o1 : o0;
+            const float2 va = unpack2(m[p][2 * j]), vb = unpack2(m[p][2 * j + 1]);
+            const float4 v = make_float4(va.x, va.y, vb.x, vb.y);
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(ah + off) = v;
+            *reinterpret_cast<float4*>(al + off) = l;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&afull[s]);
+        }
+      }
+    }
+   } else {
+    // ------------------------------------------------------------------ consumers, any K (16 warps x 8 rows)
     const int wc = warp - 2;      // consumer warp: rows 8*wc .. 8*wc+7 of the tile
     const int seg = lane & 3;     // this thread's channels: 4seg..4seg+3 and 16+4seg..16+4seg+3 of the group
     const int r = 8 * wc + (lane >> 2);
@@ -302,11 +439,13 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
           }
         }
     }
+   }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 18..21)
     const int q = warp & 3;
     const int et = threadIdx.x - 576;  // 0..127
-    uint8_t* my_stage = out_stage + (warp - 18) * 4096;
+    constexpr int OR = Cfg::kOutRows;                   // rows per TMA store: 32, or 16 in two passes
+    uint8_t* my_stage = out_stage + (warp - 18) * (OR * 128);
     uint32_t tile = 0;
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
       for (int nt = 0; nt < num_nt; ++nt, ++tile) {
@@ -337,17 +476,23 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               v[j] = tc_act(fmaf(__uint_as_float(rg[j]), prm[c0e + j], prm[BN + c0e + j]), a.act);
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmY, my_stage, nt * BN + c0e, mt * kTcBM + q * 32);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int pass = 0; pass < 32 / OR; ++pass) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+              if (lane / OR == pass) {
+                const int rl = lane % OR;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(my_stage + rl * 128 + ((j ^ (rl & 7)) << 4)) =
+                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmY, my_stage, nt * BN + c0e, mt * kTcBM + q * 32 + pass * OR);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              }
             }
           }
         }
@@ -365,21 +510,22 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
   }
 }
 
-template <int BN>
+template <int BN, bool K8>
 static int launch_ca(const CAArgs& a, const float* thi, const float* tlo, float* out, cudaStream_t st) {
+  using Cfg = CACfg<BN, K8>;
   CUtensorMap mh, ml, my;
   int rc;
   const int Kd = 4 * a.Din;
   if ((rc = make_map(&mh, thi, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
   if ((rc = make_map(&ml, tlo, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
-  if ((rc = make_map(&my, out, a.rows, a.Dout, a.Dout, 32)) != DH3D_OK) return rc;
-  auto kern = flexconv_ca_kernel<BN>;
+  if ((rc = make_map(&my, out, a.rows, a.Dout, a.Dout, Cfg::kOutRows)) != DH3D_OK) return rc;
+  auto kern = flexconv_ca_kernel<BN, K8>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)CACfg<BN>::kSmemBytes);
+                                       (int)Cfg::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   const int num_mt = ceil_div(a.rows, kTcBM);
   const int grid = num_mt < num_sms() ? num_mt : num_sms();
-  kern<<<grid, kCAThreads, CACfg<BN>::kSmemBytes, st>>>(mh, ml, my, a);
+  kern<<<grid, kCAThreads, Cfg::kSmemBytes, st>>>(mh, ml, my, a);
   return launch_status();
 }
 
@@ -392,8 +538,14 @@ int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, 
   const float* thi = reinterpret_cast<const float*>(theta_packed);
   const float* tlo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(theta_packed) +
                                                     align_up((size_t)4 * Din * Dout * sizeof(float), 256));
-  if (Dout <= 64) return launch_ca<64>(a, thi, tlo, out, st);
-  return launch_ca<128>(a, thi, tlo, out, st);
+  // DH3D_FLEXCONV_K8=0 sends K == 8 through the generic consumer loop (A/B comparison)
+  static const bool k8_off = getenv("DH3D_FLEXCONV_K8") && getenv("DH3D_FLEXCONV_K8")[0] == '0';
+  if (K == 8 && !k8_off && ((uintptr_t)nbr & 7) == 0) {
+    if (Dout <= 64) return launch_ca<64, true>(a, thi, tlo, out, st);
+    return launch_ca<128, true>(a, thi, tlo, out, st);
+  }
+  if (Dout <= 64) return launch_ca<64, false>(a, thi, tlo, out, st);
+  return launch_ca<128, false>(a, thi, tlo, out, st);
 }
 
 }  // namespace dh3d

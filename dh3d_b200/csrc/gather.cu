@@ -9,6 +9,8 @@
 // strided by N).  These are HBM/L2-bandwidth ops: no shared-memory staging except where a tile is
 // re-read by every thread (three_nn, query_ball_point).
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -371,6 +373,60 @@ __global__ void three_interp_kernel(const float* __restrict__ points, const int3
   }
 }
 
+// Warp-per-row form (c % 4 == 0): the element-per-thread kernel above recomputes the three weights (five
+// IEEE divisions with FROM_DIST) and re-reads idx / w in each of the c/4 threads of a row, which made the op
+// issue-bound at a quarter of the HBM write roofline (ncu r1j: 171 us for 32 x 8192 x 256).  Here lanes
+// 0..23 of a warp load idx / w of 8 consecutive rows (one element each) and do the divisions once; the
+// warp then walks the 8 rows, lanes covering the channels with 16-byte accesses.  Same arithmetic, same order.
+template <bool FROM_DIST>
+__global__ void __launch_bounds__(256)
+three_interp_warp_kernel(const float* __restrict__ points, const int32_t* __restrict__ idx,
+                         const float* __restrict__ wsrc, float* __restrict__ out, long long rows, int n,
+                         int m, int c, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int sub = lane / 3;              // row of the group (valid for lane < 24)
+  const int el = lane - sub * 3;
+  const int l0 = sub < 8 ? sub * 3 : 0;  // first lane of this lane's row
+  for (long long r0 = warp0 * 8; r0 < rows; r0 += nwarps * 8) {
+    const long long rr = r0 + sub;
+    float w = 1.f;
+    int id = 0;
+    long long pbase = 0;
+    if (lane < 24 && rr < rows) {
+      w = __ldg(wsrc + rr * 3 + el);
+      id = __ldg(idx + rr * 3 + el);
+      pbase = ((rr / n) * m + id) * (long long)c;   // float offset of the source row
+    }
+    if constexpr (FROM_DIST) {
+      const float v = __fdiv_rn(1.f, fmaxf(w, 1e-10f));
+      const float v1 = __shfl_sync(0xffffffffu, v, l0), v2 = __shfl_sync(0xffffffffu, v, l0 + 1),
+                  v3 = __shfl_sync(0xffffffffu, v, l0 + 2);
+      w = __fdiv_rn(v, __fadd_rn(__fadd_rn(v1, v2), v3));
+    }
+    const int nr = (int)(rows - r0 < 8 ? rows - r0 : 8);
+#pragma unroll 2
+    for (int j = 0; j < nr; ++j) {
+      const float w1 = __shfl_sync(0xffffffffu, w, 3 * j), w2 = __shfl_sync(0xffffffffu, w, 3 * j + 1),
+                  w3 = __shfl_sync(0xffffffffu, w, 3 * j + 2);
+      const float* p1 = points + __shfl_sync(0xffffffffu, pbase, 3 * j);
+      const float* p2 = points + __shfl_sync(0xffffffffu, pbase, 3 * j + 1);
+      const float* p3 = points + __shfl_sync(0xffffffffu, pbase, 3 * j + 2);
+      float* o = out + (r0 + j) * ldo;
+      for (int col = lane * 4; col < c; col += 128) {
+        const float4 a = ldg4(p1 + col), bb = ldg4(p2 + col), cc = ldg4(p3 + col);
+        float4 v;
+        v.x = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w1), __fmul_rn(bb.x, w2)), __fmul_rn(cc.x, w3));
+        v.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(bb.y, w2)), __fmul_rn(cc.y, w3));
+        v.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(bb.z, w2)), __fmul_rn(cc.z, w3));
+        v.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(bb.w, w2)), __fmul_rn(cc.w, w3));
+        *reinterpret_cast<float4*>(o + col) = v;
+      }
+    }
+  }
+}
+
 // ldo = row stride of `out` in floats (>= c): the result may land in a column block of a wider tensor (fused concat)
 int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
                                 const float* wsrc, float* out, int ldo, bool from_dist, cudaStream_t st);
@@ -387,6 +443,15 @@ int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points,
 #define DH3D_TI(V, FD)                                                                          \
   three_interp_kernel<V, FD><<<ew_blocks(rows * (c / V), 256), 256, 0, st>>>(points, idx, wsrc, out, \
                                                                             rows, n, m, c, ldo)
+  static const bool elementwise = getenv("DH3D_INTERP") && !strcmp(getenv("DH3D_INTERP"), "elem");
+  if (vec && !elementwise) {
+    const int blocks = ew_blocks(((rows + 7) / 8) * 32, 256);
+    if (from_dist)
+      three_interp_warp_kernel<true><<<blocks, 256, 0, st>>>(points, idx, wsrc, out, rows, n, m, c, ldo);
+    else
+      three_interp_warp_kernel<false><<<blocks, 256, 0, st>>>(points, idx, wsrc, out, rows, n, m, c, ldo);
+    return launch_status();
+  }
   if (vec) { if (from_dist) DH3D_TI(4, true); else DH3D_TI(4, false); }
   else { if (from_dist) DH3D_TI(1, true); else DH3D_TI(1, false); }
 #undef DH3D_TI

@@ -283,6 +283,19 @@ def se_excite(x, gate):
     return y
 
 
+def se_pool_excite(x, neighborhood, w1, b1, w2, b2):
+    """relu(x + x * sigmoid(relu(flex_pool(x, nbr) @ w1 + b1) @ w2 + b2)) in one launch
+    (se_res_bottleneck, core/backbones.py:45-55).  x [B,N,C], neighborhood [B,N,K], C in {64,128}, H = C/4."""
+    B, N, C = x.shape
+    K = neighborhood.shape[2]
+    H = w1.shape[1]
+    y = torch.empty_like(x)
+    call("dh3d_se_pool_excite", check(x, f32, "x", 3), check(neighborhood, i32, "neighborhood", 3),
+         check(w1, f32, "w1", 2), check(b1, f32, "b1"), check(w2, f32, "w2", 2), check(b2, f32, "b2"),
+         check(y, f32, "y"), B, N, K, C, H, stream_ptr(x.device))
+    return y
+
+
 def add(a, b):
     y = torch.empty_like(a)
     call("dh3d_add", check(a, f32, "a"), check(b, f32, "b"), check(y, f32, "y"), _cs(a.numel()),

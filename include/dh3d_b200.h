@@ -185,6 +185,14 @@ DH3D_API int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* pack
 DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream);
 DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);
+/* Whole se_res_bottleneck of flex_conv_dilate in one launch (core/backbones.py:45-55 called at :84-88 with
+ * add_se='max_pool'): y = relu(x + x * sigmoid(W2^T relu(W1^T flex_pool(x, nbr) + b1) + b2)).
+ *   x, y [B,N,C] point-major; neighborhood [B,N,K] int32 (ids within the cloud); w1 [C,H], b1 [H], w2 [H,C],
+ *   b2 [C] (the two feature_conv1d_1 layers, no BN).  C in {64,128} and H == C/4 (DH3D's shapes), otherwise
+ *   DH3D_ERR_UNSUPPORTED and the caller composes dh3d_flex_pool_pm / dh3d_linear / dh3d_se_excite. */
+DH3D_API int dh3d_se_pool_excite(const float* x, const int32_t* neighborhood, const float* w1, const float* b1,
+                        const float* w2, const float* b2, float* y, int B, int N, int K, int C, int H,
+                        void* stream);
 DH3D_API int dh3d_l2_normalize_rows(const float* x, int ldx, float* y, int ldy, int M, int C, float eps,
                            void* stream);
 DH3D_API int dh3d_add(const float* a, const float* b, float* y, size_t count, void* stream);

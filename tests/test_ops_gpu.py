@@ -208,7 +208,8 @@ def test_flex_conv_reference_fixture_odd_dims():
 @pytest.mark.parametrize("B,N,K,Din,Dout", [(2, 1024, 8, 32, 64), (1, 8192, 8, 64, 64), (2, 1024, 8, 64, 128),
                                             (2, 1024, 8, 128, 128), (1, 1024, 8, 128, 256), (1, 2048, 16, 128, 128),
                                             (1, 512, 32, 128, 128), (1, 300, 5, 8, 12), (3, 333, 8, 32, 64),
-                                            (2, 777, 11, 64, 72)])
+                                            (2, 777, 11, 64, 72), (3, 333, 8, 64, 64), (2, 777, 8, 128, 200),
+                                            (5, 8192, 8, 64, 64), (3, 8192, 8, 64, 128)])
 def test_flex_conv_pm_vs_fp64_truth(B, N, K, Din, Dout):
     from dh3d_b200 import ops
     rng = np.random.RandomState(N + Din + Dout + K)
@@ -290,7 +291,7 @@ def test_three_nn_bitexact(B, n, m):
 def test_three_interpolate_bitexact_and_fused_weights():
     from dh3d_b200 import ops, tf_ops
     rng = np.random.RandomState(31)
-    for C in (128, 256, 5):
+    for C in (128, 256, 5, 12, 192):
         pts = rng.randn(2, 100, C).astype(np.float32)
         idx = rng.randint(0, 100, (2, 999, 3)).astype(np.int32)
         dist = (rng.rand(2, 999, 3) * 4).astype(np.float32)
@@ -357,6 +358,31 @@ def test_small_glue_ops():
     t = rng.randn(2, 5, 77).astype(np.float32)
     assert np.array_equal(ops.transpose_cm_to_pm(cu(t)).cpu().numpy(), t.transpose(0, 2, 1))
     assert np.array_equal(ops.transpose_pm_to_cm(cu(t)).cpu().numpy(), t.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("B,N,K,C", [(2, 1000, 8, 64), (3, 333, 8, 64), (1, 77, 5, 64), (2, 500, 8, 128),
+                                     (1, 129, 3, 128), (2, 8192, 8, 64)])
+def test_se_pool_excite_fused_vs_fp64_and_unfused(B, N, K, C):
+    # se_res_bottleneck (core/backbones.py:45-55): fused launch vs the fp64 composition and vs the separate ops
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(B * 7 + N + K + C)
+    H = C // 4
+    x = rng.randn(B, N, C).astype(np.float32)
+    nbr = rng.randint(0, N, (B, N, K)).astype(np.int32)
+    w1, b1 = (rng.randn(C, H) / np.sqrt(C)).astype(np.float32), rng.randn(H).astype(np.float32) * 0.1
+    w2, b2 = (rng.randn(H, C) / np.sqrt(H)).astype(np.float32), rng.randn(C).astype(np.float32) * 0.1
+    b1, b2 = b1.astype(np.float32), b2.astype(np.float32)
+    pooled = np.stack([x[b][nbr[b]].max(axis=1) for b in range(B)]).astype(np.float64)
+    hid = np.maximum(pooled @ w1.astype(np.float64) + b1, 0)
+    gate = 1 / (1 + np.exp(-(hid @ w2.astype(np.float64) + b2)))
+    want = np.maximum(x + x * gate, 0)
+    got = ops.se_pool_excite(cu(x), cu(nbr), cu(w1), cu(b1), cu(w2), cu(b2))
+    close(got, want, rel=2e-5)
+    mx = ops.flex_pool(cu(x), cu(nbr))
+    mx = mx[0] if isinstance(mx, tuple) else mx
+    assert np.array_equal(mx.cpu().numpy(), pooled.astype(np.float32))
+    unf = ops.se_excite(cu(x), ops.linear(ops.linear(mx, cu(w1), shift=cu(b1), act=1), cu(w2), shift=cu(b2), act=2))
+    close(got, unf.cpu().numpy(), rel=2e-5)
 
 
 @pytest.mark.parametrize("B,N", [(2, 8192), (3, 1000), (1, 37)])

@@ -26,6 +26,10 @@ _SIGNATURES = {
     "dh3d_flex_conv": (_c_int, [_p] * 6 + [_c_int] * 5 + [_p, _c_size_t, _p]),
     "dh3d_flex_conv_pm_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "dh3d_flex_conv_pm": (_c_int, [_p] * 6 + [_c_int] * 5 + [_p, _p, _p, _c_int, _p, _c_size_t, _p]),
+    "dh3d_flex_conv_prepack_bytes": (_c_size_t, [_c_int] * 2),
+    "dh3d_flex_conv_prepack": (_c_int, [_p] * 5 + [_c_int] * 2 + [_p, _p]),
+    "dh3d_flex_conv_pm_packed_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "dh3d_flex_conv_pm_packed": (_c_int, [_p] * 5 + [_c_int] * 5 + [_p, _c_int, _p, _c_size_t, _p]),
     "dh3d_flex_pool": (_c_int, [_p] * 4 + [_c_int] * 4 + [_p]),
     "dh3d_flex_pool_pm": (_c_int, [_p] * 4 + [_c_int] * 4 + [_p]),
     "dh3d_conv_pointset": (_c_int, [_p] * 5 + [_c_int] * 5 + [_p]),
@@ -84,7 +88,8 @@ _lib = None
 _KERNELS_PER_CALL = {
     "dh3d_knn_bruteforce": 2, "dh3d_knn_bruteforce_pm": 2,          # pack + scan
     "dh3d_flex_conv": 8,                                             # 4 transposes + theta_ext + moments + gemm (+memset)
-    "dh3d_flex_conv_pm": 3,                                          # theta_ext + moments + gemm (+1 if feature_bias)
+    "dh3d_flex_conv_pm": 3,                                          # theta_ext + fold_bias + the fused kernel
+    "dh3d_flex_conv_prepack": 2, "dh3d_flex_conv_pm_packed": 1,      # weights once; then the fused kernel only
     "dh3d_query_ball_point": 2, "dh3d_netvlad": 4, "dh3d_three_nn_ws": 3,
     "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
     "dh3d_keypoint_nms": 5,

@@ -73,6 +73,13 @@ int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const
                               const float* shift, int act, const float* w2, float b2, int act2, float* y2,
                               int M, int K, int N, cudaStream_t st);
 // flexconv.cu
+size_t flex_conv_prepack_bytes(int Din, int Dout);
+int flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias, const float* scale,
+                      const float* shift, int Din, int Dout, void* packed, cudaStream_t st);
+size_t flex_conv_pm_packed_workspace_bytes(int B, int N, int K, int Din, int Dout);
+int flex_conv_pm_packed(const float* feat, const void* packed, const int32_t* nbr, const float* xyz, float* out,
+                        int B, int N, int K, int Din, int Dout, const float* scale, int act, void* ws,
+                        size_t ws_bytes, cudaStream_t st);
 size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout);
 size_t flex_conv_cm_workspace_bytes(int B, int N, int K, int Din, int Dout);
 int flex_conv_pm(const float* feat, const float* theta, const float* bias, const int32_t* nbr,
@@ -191,6 +198,21 @@ int dh3d_flex_conv(const float* features_cm, const float* theta, const float* bi
                    void* stream) {
   return flex_conv_cm(features_cm, theta, bias, neighborhood_cm, positions_cm, out_cm, B, N, K, Din,
                       Dout, workspace, workspace_bytes, S(stream));
+}
+size_t dh3d_flex_conv_prepack_bytes(int Din, int Dout) { return flex_conv_prepack_bytes(Din, Dout); }
+int dh3d_flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias, const float* scale,
+                           const float* shift, int Din, int Dout, void* packed, void* stream) {
+  return flex_conv_prepack(theta, bias, feature_bias, scale, shift, Din, Dout, packed, S(stream));
+}
+size_t dh3d_flex_conv_pm_packed_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  return flex_conv_pm_packed_workspace_bytes(B, N, K, Din, Dout);
+}
+int dh3d_flex_conv_pm_packed(const float* features_pm, const void* packed, const int32_t* neighborhood_pm,
+                             const float* xyz_pm, float* out_pm, int B, int N, int K, int Din, int Dout,
+                             const float* scale, int act, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  return flex_conv_pm_packed(features_pm, packed, neighborhood_pm, xyz_pm, out_pm, B, N, K, Din, Dout, scale,
+                             act, workspace, workspace_bytes, S(stream));
 }
 size_t dh3d_flex_conv_pm_workspace_bytes(int B, int N, int K, int Din, int Dout) {
   return flex_conv_pm_total_workspace_bytes(B, N, K, Din, Dout);

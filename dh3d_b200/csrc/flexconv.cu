@@ -149,6 +149,72 @@ size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout
   return base ? base + align_up((size_t)Dout * sizeof(float), 256) : 0;
 }
 
+// ---- weight-only preparation (Theta_ext in the contraction's operand form + the folded shift) ----------
+// packed = [Theta_ext (plain, or {hi^T, lo^T} for the tensor-core path) | fshift[Dout]].  Depends on the
+// layer's weights only, so an inference caller prepares it once (dh3d_flex_conv_prepack) instead of
+// re-deriving it in every forward (two extra launches per layer, ~6 us each with their gaps).
+size_t flex_conv_prepack_bytes(int Din, int Dout) {
+  if (Din <= 0 || Dout <= 0) return 0;
+  return theta_ext_bytes(Din, Dout) + align_up((size_t)Dout * sizeof(float), 256);
+}
+
+static int flex_conv_prepack_padded(const float* theta, const float* bias, const float* feature_bias,
+                                    const float* scale, const float* shift, int Din, int Dout,
+                                    int din_logical, int dout_logical, void* packed, cudaStream_t st) {
+  float* theta_ext = reinterpret_cast<float*>(packed);
+  float* fshift = reinterpret_cast<float*>(reinterpret_cast<char*>(packed) + theta_ext_bytes(Din, Dout));
+  // Theta_ext = [bias ; theta_x ; theta_y ; theta_z]  (logical dims may be smaller than the padded ones)
+  if (gemm_use_tc()) {
+    float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) +
+                                         align_up((size_t)4 * Din * Dout * sizeof(float), 256));
+    theta_ext_packed_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(
+        theta, bias, theta_ext, lo, din_logical, dout_logical, Din, Dout);
+  } else {
+    theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
+                                                                   dout_logical, Din, Dout);
+  }
+  fold_bias_kernel<<<ceil_div(Dout, 128), 128, 0, st>>>(feature_bias, scale, shift, fshift, Dout);
+  return launch_status();
+}
+
+int flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias, const float* scale,
+                      const float* shift, int Din, int Dout, void* packed, cudaStream_t st) {
+  if (!theta || !bias || !packed) return DH3D_ERR_NULL;
+  if (Din <= 0 || Dout <= 0) return DH3D_ERR_DIM;
+  if (Din % 4 || Dout % 4) return DH3D_ERR_UNSUPPORTED;
+  if (((uintptr_t)packed & 255) != 0) return DH3D_ERR_ALIGN;
+  return flex_conv_prepack_padded(theta, bias, feature_bias, scale, shift, Din, Dout, Din, Dout, packed, st);
+}
+
+static int flex_conv_run(const float* feat, const float* theta_ext, const float* eff_shift, const int32_t* nbr,
+                         const float* xyz, float* out, int B, int N, int K, int Din, int Dout,
+                         const float* scale, int act, float* A, cudaStream_t st);
+
+size_t flex_conv_pm_packed_workspace_bytes(int B, int N, int K, int Din, int Dout) {
+  (void)K;
+  if (B <= 0 || N <= 0 || Din <= 0 || Dout <= 0) return 0;
+  // only the two-kernel form (DH3D_FLEXCONV=split / DH3D_GEMM=simt / unsupported dims) needs the moment matrix
+  if (gemm_use_tc() && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) return 256;
+  return moments_bytes(B, N, Din);
+}
+
+// scale must be the one given to flex_conv_prepack (the shift is already inside `packed`)
+int flex_conv_pm_packed(const float* feat, const void* packed, const int32_t* nbr, const float* xyz, float* out,
+                        int B, int N, int K, int Din, int Dout, const float* scale, int act, void* ws,
+                        size_t ws_bytes, cudaStream_t st) {
+  if (!feat || !packed || !nbr || !xyz || !out) return DH3D_ERR_NULL;
+  if (B <= 0 || N <= 0 || K <= 0 || Din <= 0 || Dout <= 0) return DH3D_ERR_DIM;
+  if (Din % 4 || Dout % 4 || K > 64) return DH3D_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < flex_conv_pm_packed_workspace_bytes(B, N, K, Din, Dout)) return DH3D_ERR_WORKSPACE;
+  if ((((uintptr_t)feat | (uintptr_t)out | (uintptr_t)ws) & 15) != 0 || ((uintptr_t)packed & 255) != 0)
+    return DH3D_ERR_ALIGN;
+  const float* theta_ext = reinterpret_cast<const float*>(packed);
+  const float* fshift =
+      reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + theta_ext_bytes(Din, Dout));
+  return flex_conv_run(feat, theta_ext, fshift, nbr, xyz, out, B, N, K, Din, Dout, scale, act,
+                       reinterpret_cast<float*>(ws), st);
+}
+
 // Din/Dout are the (4-aligned) dims of feat/out; theta/bias have the logical dims
 // din_logical x dout_logical (equal to Din/Dout except for the padded channel-major entry).
 int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias,
@@ -166,34 +232,26 @@ int flex_conv_pm_padded(const float* feat, const float* theta, const float* bias
   char* p = reinterpret_cast<char*>(ws);
   float* A = reinterpret_cast<float*>(p);
   p += moments_bytes(B, N, Din);
-  float* theta_ext = reinterpret_cast<float*>(p);
-  p += theta_ext_bytes(Din, Dout);
-  float* fshift = reinterpret_cast<float*>(p);
+  void* packed = p;   // [Theta_ext | fshift], the layout flex_conv_prepack writes
+  int rc = flex_conv_prepack_padded(theta, bias, feature_bias, scale, shift, Din, Dout, din_logical,
+                                    dout_logical, packed, st);
+  if (rc != DH3D_OK) return rc;
+  const float* theta_ext = reinterpret_cast<const float*>(packed);
+  const float* fshift = reinterpret_cast<const float*>(p + theta_ext_bytes(Din, Dout));
+  return flex_conv_run(feat, theta_ext, fshift, nbr, xyz, out, B, N, K, Din, Dout, scale, act, A, st);
+}
 
-  // Theta_ext = [bias ; theta_x ; theta_y ; theta_z]  (logical dims may be smaller than the padded ones)
+static int flex_conv_run(const float* feat, const float* theta_ext_c, const float* eff_shift, const int32_t* nbr,
+                         const float* xyz, float* out, int B, int N, int K, int Din, int Dout,
+                         const float* scale, int act, float* A, cudaStream_t st) {
+  float* theta_ext = const_cast<float*>(theta_ext_c);   // the launchers take non-const operand pointers
   const bool tc = gemm_use_tc();
-  if (tc) {
-    float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) +
-                                         align_up((size_t)4 * Din * Dout * sizeof(float), 256));
-    theta_ext_packed_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(
-        theta, bias, theta_ext, lo, din_logical, dout_logical, Din, Dout);
-  } else {
-    theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
-                                                                   dout_logical, Din, Dout);
-  }
-
-  const float* eff_shift = shift;
-  if (feature_bias) {
-    fold_bias_kernel<<<ceil_div(Dout, 128), 128, 0, st>>>(feature_bias, scale, shift, fshift, Dout);
-    eff_shift = fshift;
-  }
-
   const long long rows = (long long)B * N;
   if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
   if (tc && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) {
-    // measured (B200, r1h): cp.async staging wins for Din >= 64 (0.2125 vs 0.2216 ms at 64->64 x 262144 points,
-    // 0.111 vs 0.130 ms at 128->256 x 32768), the per-thread gather for Din = 32 (0.122 vs 0.139 ms)
-    static const int ca_min_din = getenv("DH3D_FLEXCONV_CA_MIN_DIN") ? atoi(getenv("DH3D_FLEXCONV_CA_MIN_DIN")) : 64;
+    // measured (B200, r1o, 32 x 8192 points, K = 8): cp.async staging with the unrolled K == 8 schedule
+    // 0.171 ms at 64->64 (0.207 generic loop) and 0.112 ms at 32->64 (per-thread gather: 0.121 ms)
+    static const int ca_min_din = getenv("DH3D_FLEXCONV_CA_MIN_DIN") ? atoi(getenv("DH3D_FLEXCONV_CA_MIN_DIN")) : 32;
     if (flexconv_mode() == 0 && Din >= ca_min_din)
       return flexconv_ca_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
                                 Dout, st);

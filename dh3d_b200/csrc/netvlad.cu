@@ -135,64 +135,60 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
   if (tid < kVK) part_s[((long long)b * slabs + slab) * kVK + tid] = ssum;
 }
 
-// one CTA per cloud: combine slabs, subtract S*W2, intra-normalise per cluster, flatten
-// feature-major ([d*64 + k], backbones.py:258-260), global l2-normalise.
+// CTA (b, q): clusters 16q .. 16q+15 of cloud b; thread = feature d.  Combines the slabs, subtracts S*W2,
+// intra-normalises each cluster column (over the 256 features, inside the CTA) and writes the feature-major
+// flattening ([d*64 + k], backbones.py:258-260).  The global l2 norm of the flattened vector only needs the 64
+// column norms: they go to coln[b][k] and the scalar is applied after the (linear) projection, in the head
+// kernel -- which lets four CTAs per cloud run here instead of one (r1o: 52 us for 32 CTAs, latency-bound).
+constexpr int kVQ = 16;
 __global__ void __launch_bounds__(kVD)
 netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restrict__ part_s, int slabs,
-                        const float* __restrict__ cw2, float* __restrict__ vlad) {
-  __shared__ float s_sum[kVK];
-  __shared__ float s_red[kVD / 32][kVK];
-  __shared__ float s_inv[kVK];
-  __shared__ float s_tot;
+                        const float* __restrict__ cw2, float* __restrict__ vlad, float* __restrict__ coln) {
+  __shared__ float s_sum[kVQ];
+  __shared__ float s_red[kVD / 32][kVQ];
+  __shared__ float s_inv[kVQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, k0 = blockIdx.y * kVQ;
 
-  if (tid < kVK) {
+  if (tid < kVQ) {
     float s = 0.f;
-    for (int c = 0; c < slabs; ++c) s += part_s[((long long)b * slabs + c) * kVK + tid];
+    for (int c = 0; c < slabs; ++c) s += part_s[((long long)b * slabs + c) * kVK + k0 + tid];
     s_sum[tid] = s;
   }
-  float v[kVK];
+  float v[kVQ];
 #pragma unroll
-  for (int k = 0; k < kVK; ++k) v[k] = 0.f;
+  for (int k = 0; k < kVQ; ++k) v[k] = 0.f;
+#pragma unroll 4
   for (int c = 0; c < slabs; ++c) {
-    const float* pv = part_v + (((long long)b * slabs + c) * kVD + tid) * kVK;
+    const float* pv = part_v + (((long long)b * slabs + c) * kVD + tid) * kVK + k0;
 #pragma unroll
-    for (int k = 0; k < kVK; k += 4) {
+    for (int k = 0; k < kVQ; k += 4) {
       const float4 t = ldg4(pv + k);
       v[k] += t.x; v[k + 1] += t.y; v[k + 2] += t.z; v[k + 3] += t.w;
     }
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < kVK; ++k) {
-    v[k] -= s_sum[k] * __ldg(cw2 + tid * kVK + k);
+  for (int k = 0; k < kVQ; ++k) {
+    v[k] -= s_sum[k] * __ldg(cw2 + tid * kVK + k0 + k);
     const float ss = warp_sum(v[k] * v[k]);
     if (lane == 0) s_red[warp][k] = ss;
   }
   __syncthreads();
-  if (tid < kVK) {
+  if (tid < kVQ) {
     float ss = 0.f;
 #pragma unroll
     for (int w = 0; w < kVD / 32; ++w) ss += s_red[w][tid];
     const float inv = rsqrtf(fmaxf(ss, 1e-12f));
     s_inv[tid] = inv;
-    s_red[0][tid] = ss * inv * inv;  // squared norm of the normalised cluster column
+    coln[(long long)b * kVK + k0 + tid] = ss * inv * inv;  // squared norm of the normalised cluster column
   }
   __syncthreads();
-  if (tid == 0) {
-    float tot = 0.f;
-    for (int k = 0; k < kVK; ++k) tot += s_red[0][k];
-    s_tot = rsqrtf(fmaxf(tot, 1e-12f));
-  }
-  __syncthreads();
-  const float g = s_tot;
-  float* o = vlad + ((long long)b * kVD + tid) * kVK;
+  float* o = vlad + ((long long)b * kVD + tid) * kVK + k0;
 #pragma unroll
-  for (int k = 0; k < kVK; k += 4)
+  for (int k = 0; k < kVQ; k += 4)
     *reinterpret_cast<float4*>(o + k) =
-        make_float4(v[k] * s_inv[k] * g, v[k + 1] * s_inv[k + 1] * g, v[k + 2] * s_inv[k + 2] * g,
-                    v[k + 3] * s_inv[k + 3] * g);
+        make_float4(v[k] * s_inv[k], v[k + 1] * s_inv[k + 1], v[k + 2] * s_inv[k + 2], v[k + 3] * s_inv[k + 3]);
 }
 
 // split-K projection: CTA s handles rows [s*128, s*128+128) of hidden1_weights [16384, 256] for a
@@ -200,48 +196,64 @@ netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restric
 __global__ void __launch_bounds__(kVD)
 netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__ hw, int B, int KD,
                        float* __restrict__ part_h) {
-  __shared__ float s_x[32][kVSlice];
+  __shared__ __align__(16) float s_x[32][kVSlice];
   const int tid = threadIdx.x;
   const int slice = blockIdx.x;
   const int b0 = blockIdx.y * 32;
   const int nb = min(32, B - b0);
-  for (int i = tid; i < nb * kVSlice; i += kVD) {
+  for (int i = tid; i < 32 * kVSlice; i += kVD) {
     const int bb = i / kVSlice, r = i % kVSlice;
-    s_x[bb][r] = __ldg(vlad + (long long)(b0 + bb) * KD + (long long)slice * kVSlice + r);
+    s_x[bb][r] = bb < nb ? __ldg(vlad + (long long)(b0 + bb) * KD + (long long)slice * kVSlice + r) : 0.f;
   }
   __syncthreads();
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
-#pragma unroll 4
-  for (int r = 0; r < kVSlice; ++r) {
-    const float wv = __ldg(w + (long long)r * kVD);
+#pragma unroll 2
+  for (int r = 0; r < kVSlice; r += 4) {   // one broadcast LDS.128 feeds four FMAs (was one LDS per FMA)
+    const float w0 = __ldg(w + (long long)r * kVD), w1 = __ldg(w + (long long)(r + 1) * kVD),
+                w2 = __ldg(w + (long long)(r + 2) * kVD), w3 = __ldg(w + (long long)(r + 3) * kVD);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = fmaf(s_x[i][r], wv, acc[i]);
+    for (int i = 0; i < 32; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(&s_x[i][r]);
+      acc[i] = fmaf(x.x, w0, acc[i]);
+      acc[i] = fmaf(x.y, w1, acc[i]);
+      acc[i] = fmaf(x.z, w2, acc[i]);
+      acc[i] = fmaf(x.w, w3, acc[i]);
+    }
   }
   for (int i = 0; i < nb; ++i)
     part_h[((long long)slice * B + b0 + i) * kVD + tid] = acc[i];
 }
 
-// one CTA per cloud: sum slices -> BN -> context gating (256x256 matvec, BN, sigmoid) -> optional
-// final l2-normalise (core/model.py:205, epsilon 1e-8).
+// one CTA per cloud: sum slices, apply the global l2 norm of the flattened VLAD (from the column norms) ->
+// BN -> context gating (256x256 matvec, BN, sigmoid) -> optional final l2-normalise (core/model.py:205,
+// epsilon 1e-8).
 __global__ void __launch_bounds__(kVD)
-netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B,
+netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B, const float* __restrict__ coln,
                     const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                     const float* __restrict__ gw, const float* __restrict__ g_scale,
                     const float* __restrict__ g_shift, int final_l2norm, float* __restrict__ out) {
   __shared__ float s_h[kVD];
   __shared__ float s_red[kVD / 32];
+  __shared__ float s_g[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
+  if (tid < kVK) {
+    const float t = warp_sum(__ldg(coln + (long long)b * kVK + tid));
+    if (lane == 0) s_g[warp] = t;
+  }
   float h = 0.f;
+#pragma unroll 16
   for (int s = 0; s < slices; ++s) h += part_h[((long long)s * B + b) * kVD + tid];
+  __syncthreads();
+  h *= rsqrtf(fmaxf(s_g[0] + s_g[1], 1e-12f));
   h = fmaf(h, __ldg(bn_scale + tid), __ldg(bn_shift + tid));
   s_h[tid] = h;
   __syncthreads();
   float g = 0.f;
-#pragma unroll 8
+#pragma unroll 16
   for (int i = 0; i < kVD; ++i) g = fmaf(s_h[i], __ldg(gw + i * kVD + tid), g);
   g = fmaf(g, __ldg(g_scale + tid), __ldg(g_shift + tid));
   float y = h * (1.f / (1.f + __expf(-g)));
@@ -260,6 +272,7 @@ netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B,
 static size_t nv_part_v_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVD * kVK * 4, 256); }
 static size_t nv_part_s_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVK * 4, 256); }
 static size_t nv_vlad_bytes(int B) { return align_up((size_t)B * kVD * kVK * 4, 256); }
+static size_t nv_coln_bytes(int B) { return align_up((size_t)B * kVK * 4, 256); }
 static size_t nv_part_h_bytes(int B) {
   return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
 }
@@ -280,7 +293,7 @@ static bool netvlad_use_tc() {
 size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
   (void)N;
   if (B <= 0 || D != kVD || Kc != kVK || out_dim != kVD) return 0;
-  return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_part_h_bytes(B) +
+  return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_coln_bytes(B) + nv_part_h_bytes(B) +
          align_up(netvlad_tc_workspace_bytes(), 256);
 }
 
@@ -302,6 +315,7 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   float* part_v = reinterpret_cast<float*>(p); p += nv_part_v_bytes(B);
   float* part_s = reinterpret_cast<float*>(p); p += nv_part_s_bytes(B);
   float* vlad = reinterpret_cast<float*>(p); p += nv_vlad_bytes(B);
+  float* coln = reinterpret_cast<float*>(p); p += nv_coln_bytes(B);
   float* part_h = reinterpret_cast<float*>(p); p += nv_part_h_bytes(B);
   void* tc_ws = p;
 
@@ -310,12 +324,12 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
     int P = 0;
     rc = netvlad_tc_aggregate_launch(features, att, B, N, cw, cbn_scale, cbn_shift, part_v, part_s, &P, tc_ws, st);
     if (rc != DH3D_OK) return rc;
-    netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, P, cw2, vlad);
+    netvlad_finalize_kernel<<<dim3(B, kVK / kVQ), kVD, 0, st>>>(part_v, part_s, P, cw2, vlad, coln);
     if ((rc = launch_status()) != DH3D_OK) return rc;
     const int slices = kVD * kVK / kVSlice;
     netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
     if ((rc = launch_status()) != DH3D_OK) return rc;
-    netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
+    netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, coln, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
                                           final_l2norm, out);
     return launch_status();
   }
@@ -333,12 +347,12 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
       features, att, N, slabs, cw, cbn_scale, cbn_shift, part_v, part_s);
   rc = launch_status();
   if (rc != DH3D_OK) return rc;
-  netvlad_finalize_kernel<<<B, kVD, 0, st>>>(part_v, part_s, slabs, cw2, vlad);
+  netvlad_finalize_kernel<<<dim3(B, kVK / kVQ), kVD, 0, st>>>(part_v, part_s, slabs, cw2, vlad, coln);
   if ((rc = launch_status()) != DH3D_OK) return rc;
   const int slices = kVD * kVK / kVSlice;
   netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
   if ((rc = launch_status()) != DH3D_OK) return rc;
-  netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, bn_scale, bn_shift, gw, gbn_scale,
+  netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, coln, bn_scale, bn_shift, gw, gbn_scale,
                                         gbn_shift, final_l2norm, out);
   return launch_status();
 }

@@ -110,8 +110,14 @@ class FlexConvolution(nn.Module):
             if bn is not None:
                 scale, shift = bn.fold()
             fb = None if self.feature_bias is None else self.feature_bias.reshape(-1).contiguous()
-            self._folded = (fb, scale, shift)
-        fb, scale, shift = self._folded
+            # weight-only operand prepared once (dh3d_flex_conv_prepack): no per-forward packing launches
+            packed = (ops.flex_conv_prepack(self.position_theta, self.position_bias, fb, scale, shift)
+                      if self.position_theta.is_cuda and os.environ.get("DH3D_FLEXCONV_PREPACK", "1") != "0"
+                      else None)
+            self._folded = (fb, scale, shift, packed)
+        fb, scale, shift, packed = self._folded
+        if packed is not None:
+            return ops.flex_conv_packed(features, packed, neighborhoods, xyz, scale=scale, act=act)
         return ops.flex_conv(features, self.position_theta, self.position_bias, neighborhoods, xyz,
                              feature_bias=fb, scale=scale, shift=shift, act=act)
 

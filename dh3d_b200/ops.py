@@ -68,6 +68,39 @@ def flex_pool(features, neighborhood, with_argmax=False):
     return (out, arg) if with_argmax else out
 
 
+def flex_conv_prepack(theta, bias, feature_bias=None, scale=None, shift=None):
+    """theta [3,Din,Dout], bias [Din,Dout] (+ feature bias / folded BN) -> opaque weight buffer for
+    ``flex_conv_packed`` (done once per layer; the buffer remembers its (Din, Dout))."""
+    _, Din, Dout = theta.shape
+    if tuple(bias.shape) != (Din, Dout):
+        raise _lib.Dh3dError("flex_conv_prepack: bias shape %s does not match theta" % (tuple(bias.shape),))
+    packed = torch.empty(query("dh3d_flex_conv_prepack_bytes", Din, Dout), dtype=torch.uint8, device=theta.device)
+    call("dh3d_flex_conv_prepack", check(theta, f32, "theta", 3), check(bias, f32, "bias", 2),
+         opt(feature_bias, f32, "feature_bias"), opt(scale, f32, "scale"), opt(shift, f32, "shift"), Din, Dout,
+         ctypes.c_void_p(packed.data_ptr()), stream_ptr(theta.device))
+    packed._dh3d_dims = (Din, Dout)
+    return packed
+
+
+def flex_conv_packed(features, packed, neighborhood, xyz, scale=None, act=ACT_NONE):
+    """flex_conv with the weights given as flex_conv_prepack(...); ``scale`` must be the one packed."""
+    B, N, Din = features.shape
+    K = neighborhood.shape[2]
+    Dp, Dout = packed._dh3d_dims
+    if Dp != Din:
+        raise _lib.Dh3dError("flex_conv_packed: features have %d channels, weights expect %d" % (Din, Dp))
+    if tuple(neighborhood.shape[:2]) != (B, N) or tuple(xyz.shape) != (B, N, 3):
+        raise _lib.Dh3dError("flex_conv_packed: neighborhood/xyz shape mismatch")
+    out = torch.empty((B, N, Dout), dtype=f32, device=features.device)
+    ws, wp, wn = workspace(query("dh3d_flex_conv_pm_packed_workspace_bytes", B, N, K, Din, Dout), features.device)
+    _lib.stats.tag = "n%d_K%d_Ci%d_Co%d" % (B * N, K, Din, Dout)
+    call("dh3d_flex_conv_pm_packed", check(features, f32, "features"), ctypes.c_void_p(packed.data_ptr()),
+         check(neighborhood, i32, "neighborhood"), check(xyz, f32, "xyz"), check(out, f32, "out"),
+         B, N, K, Din, Dout, opt(scale, f32, "scale"), int(act), wp, wn, stream_ptr(features.device))
+    _lib.stats.tag = None
+    return out
+
+
 def conv_pointset(features, theta, bias, neighborhood, scale=None, shift=None, act=ACT_NONE):
     B, N, Din = features.shape
     K = neighborhood.shape[2]

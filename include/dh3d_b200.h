@@ -93,6 +93,22 @@ DH3D_API int dh3d_flex_conv_pm(const float* features_pm, const float* theta, con
                       int N, int K, int Din, int Dout, const float* feature_bias,
                       const float* scale, const float* shift, int act, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* Inference form with the weight-only work hoisted out of the forward (the Keras layer of the reference owns
+ * position_theta / position_bias / feature_bias, core/layers.py:252-288, and the BatchNorm that follows it,
+ * core/tf_utils.py:58-63): dh3d_flex_conv_prepack derives, once per layer, the contraction operand
+ * [position_bias; theta_x; theta_y; theta_z] in the kernel's layout plus the folded shift
+ * feature_bias*scale + shift; dh3d_flex_conv_pm_packed is dh3d_flex_conv_pm on that buffer (pass the SAME
+ * scale).  packed: dh3d_flex_conv_prepack_bytes(Din, Dout) bytes, 256-byte aligned; it depends on the
+ * DH3D_GEMM / DH3D_FLEXCONV settings of the process that made it. */
+DH3D_API size_t dh3d_flex_conv_prepack_bytes(int Din, int Dout);
+DH3D_API int dh3d_flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias,
+                           const float* scale, const float* shift, int Din, int Dout, void* packed,
+                           void* stream);
+DH3D_API size_t dh3d_flex_conv_pm_packed_workspace_bytes(int B, int N, int K, int Din, int Dout);
+DH3D_API int dh3d_flex_conv_pm_packed(const float* features_pm, const void* packed,
+                             const int32_t* neighborhood_pm, const float* xyz_pm, float* out_pm, int B,
+                             int N, int K, int Din, int Dout, const float* scale, int act,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FlexPool forward -- replaces op FlexPool

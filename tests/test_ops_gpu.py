@@ -241,6 +241,23 @@ def test_flex_conv_fused_epilogue_and_cm_entry():
     close(out_cm, exp)
 
 
+def test_flex_conv_prepacked_is_bit_identical_to_the_per_call_form():
+    # dh3d_flex_conv_prepack + dh3d_flex_conv_pm_packed == dh3d_flex_conv_pm (same kernels, weights prepared once)
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(23)
+    for (B, N, K, Din, Dout) in [(2, 1024, 8, 64, 128), (1, 777, 5, 32, 64), (1, 300, 8, 8, 12)]:
+        pts, nb, f, th, bi = _flexconv_case(rng, B, N, K, Din, Dout)
+        fb = rng.randn(Dout).astype(np.float32)
+        sc, sh = (rng.rand(Dout) + 0.5).astype(np.float32), rng.randn(Dout).astype(np.float32)
+        a = ops.flex_conv(cu(f), cu(th), cu(bi), cu(nb), cu(pts), feature_bias=cu(fb), scale=cu(sc), shift=cu(sh), act=1)
+        packed = ops.flex_conv_prepack(cu(th), cu(bi), cu(fb), cu(sc), cu(sh))
+        b = ops.flex_conv_packed(cu(f), packed, cu(nb), cu(pts), scale=cu(sc), act=1)
+        assert torch.equal(a, b)
+        a0 = ops.flex_conv(cu(f), cu(th), cu(bi), cu(nb), cu(pts))
+        b0 = ops.flex_conv_packed(cu(f), ops.flex_conv_prepack(cu(th), cu(bi)), cu(nb), cu(pts))
+        assert torch.equal(a0, b0)
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("mode", ["regs", "split", "g4"])
 def test_flex_conv_other_kernels_in_subprocess(mode):

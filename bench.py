@@ -325,7 +325,7 @@ def main():
         try:
             from dh3d_b200.model import GraphedForward
             graphs = [GraphedForward(model, dev_batches[0], outputs=outputs) for _ in range(2)]
-            graph_note = "forward replayed from a CUDA graph (53 kernels, 2 streams)"
+            graph_note = "forward replayed from a CUDA graph (%d kernels, 2 streams)"
         except Exception as e:  # noqa: BLE001 -- fall back loudly, never silently
             graphs, graph_note = None, "eager launches (graph capture failed: %s)" % str(e)[:120]
             print("bench: CUDA graph capture failed, running eagerly: %s" % e, file=sys.stderr)
@@ -370,6 +370,8 @@ def main():
     # ---- timed region: exactly K steps, inputs resident ------------------------------------------
     sampler = ClockSampler(local_rank)
     kernels_per_step = _lib.stats.kernels // 2
+    if graphs is not None:
+        graph_note = graph_note % kernels_per_step
     _lib.stats.reset()
     _lib.stats.timing_filter = {dom_name} if graphs is None else None
     barrier()

@@ -97,8 +97,10 @@ class FlexConvDilate(nn.Module):
         self.se = SEBlock(c) if add_se == "max_pool" else None
         self.concat_conv1d = FeatureConv1d(c + cin, c) if concat else None
 
-    def forward(self, xyz, feat, knn_indices=None, geometry=None, cat=None):
+    def forward(self, xyz, feat, knn_indices=None, geometry=None, cat=None, defer_concat=False):
         """xyz [B,N,3], feat [B,N,C] -> new_feat [B,N,outdims[-1]].
+        ``defer_concat`` (with ``cat``): stop before ``concat_conv1d`` and return the filled concat buffer, so the
+        caller can fuse that 1x1 layer with what follows it (LocalBackbone's join).
 
         ``cat`` (dilate > 1 with concat only): a [B,N,outdims[-1]+C] buffer whose LAST C columns already hold
         ``feat`` (written there by the producing 1x1 layer); the up-sampled features are interpolated straight
@@ -124,7 +126,7 @@ class FlexConvDilate(nn.Module):
         if self.upsample and self.dilate > 1:
             if cat is not None and self.concat_conv1d is not None:
                 ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True, out=cat, out_col=0)
-                return self.concat_conv1d(cat)
+                return cat if defer_concat else self.concat_conv1d(cat)
             x = ops.three_interpolate(x, g.nn_idx, g.nn_dist, weight_is_dist2=True)
         if self.concat_conv1d is not None:
             B, N, C = x.shape
@@ -159,6 +161,17 @@ class LocalBackbone(nn.Module):
         # stage2's concat buffer: [up-sampled 128 | before_stage2 64]; the 1x1 layer writes its block in place
         cat = torch.empty((B, N, self.stage2.outdims[-1] + 64), dtype=x1.dtype, device=x1.device)
         self.before_stage2_conv1d(x1, out=cat, out_col=self.stage2.outdims[-1])
+        # stage-2 concat layer + stage-1 shortcut + residual add (+ descriptor l2-norm): one launch
+        # (dh3d_linear_join_packed) when both weights are in the fp16-pair layout, else the separate ops
+        la, lb = self.stage2.concat_conv1d.tfconv0, self.local_stage1_shortcut.tfconv0
+        (_, sa, ba, pa), (_, sb, bb, pb) = la.folded(), lb.folded()
+        fused = (pa is not None and pb is not None and la.W.shape[3] == 128 and
+                 not os.environ.get("DH3D_GEMM_SPLIT", "f16").lower().startswith("t") and
+                 not os.environ.get("DH3D_JOIN", "fused").lower().startswith("s"))
+        if fused:
+            cat = self.stage2(points, None, geometry=geometry, cat=cat, defer_concat=True)
+            return ops.linear_join(cat, pa, sa, ba, la.act, x1, pb, sb, bb, lb.act,
+                                   eps=1e-8 if with_desc else None)
         x2 = self.stage2(points, None, geometry=geometry, cat=cat)
         sc = self.local_stage1_shortcut(x1)
         if with_desc:

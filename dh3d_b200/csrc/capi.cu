@@ -72,6 +72,10 @@ int linear_tc16_launch(const float* x, int ldx, const void* packed, const float*
 int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const float* scale,
                               const float* shift, int act, const float* w2, float b2, int act2, float* y2,
                               int M, int K, int N, cudaStream_t st);
+int linear_join_tc16_launch(const float* xa, int ldxa, const void* packed_a, const float* scale_a,
+                            const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_b,
+                            const float* scale_b, const float* shift_b, int act_b, float* y, int ldy, float* yn,
+                            int ldn, float eps, int M, int Ka, int Kb, int N, cudaStream_t st);
 // flexconv.cu
 size_t flex_conv_prepack_bytes(int Din, int Dout);
 int flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias, const float* scale,
@@ -312,6 +316,14 @@ int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, con
     return linear_rowdot_tc16_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N,
                                      S(stream));
   return linear_rowdot_tc_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
+}
+int dh3d_linear_join_packed(const float* xa, int ldxa, const void* packed_wa, const float* scale_a,
+                            const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_wb,
+                            const float* scale_b, const float* shift_b, int act_b, float* y, int ldy,
+                            float* y_normalized, int ldn, float eps, int M, int Ka, int Kb, int N, void* stream) {
+  if (!gemm_split_f16()) return DH3D_ERR_UNSUPPORTED;   // packed weights are in the 3xTF32 layout
+  return linear_join_tc16_launch(xa, ldxa, packed_wa, scale_a, shift_a, act_a, xb, ldxb, packed_wb, scale_b,
+                                 shift_b, act_b, y, ldy, y_normalized, ldn, eps, M, Ka, Kb, N, S(stream));
 }
 int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream) {

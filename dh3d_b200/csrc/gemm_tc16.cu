@@ -498,4 +498,296 @@ int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const
   return launch_t16<256, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
 }
 
+
+// ===========================================================================================================
+// Two-branch join:  y = actA((Xa @ Wa) * sA + bA) + actB((Xb @ Wb) * sB + bB),   yn = y / sqrt(max(sum y^2, eps))
+// The last step of backbone_local_dilate (core/backbones.py:121-123: stage-2 output + local_stage1_shortcut) and
+// the l2-normalised local descriptors of core/model.py:177-181.  As separate launches -- two 1x1 layers writing
+// [M,128] each, then add + l2norm reading both and writing two more -- this was 0.22 ms per 32 x 8192 step for
+// 1.2 GB of traffic; fused, each input row is read once and each output written once (536 MB).
+// Same warp roles as gemm_tc16_kernel.  Per 128-row tile the K slabs of branch A then branch B stream through the
+// same stage ring into two 128-column TMEM accumulators; all 512 TMEM columns = two tiles in flight, so the epilogue
+// of tile i (two passes over TMEM: the row norm needs the whole row first) overlaps the MMAs of tile i + 1.
+// N == 128 only (one N tile holds the whole output row, which the norm needs).
+// ===========================================================================================================
+constexpr int kJBN = 128;
+constexpr int kJStages = 4;
+struct JoinCfg {
+  static constexpr uint32_t kRawBytes = kTcBM * kTcBK * 4;
+  static constexpr uint32_t kABytes = kTcBM * kTcBK * 2;
+  static constexpr uint32_t kBBytes = kJBN * kTcBK * 2;
+  static constexpr uint32_t kStageBytes = kRawBytes + 2 * kABytes + 2 * kBBytes;
+  static constexpr uint32_t kParamBytes = 2 * 4 * kJBN * 4;   // [tile parity][sA*csA, bA, sB*csB, bB][128]
+  static constexpr uint32_t kSmemBytes =
+      kJStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+struct JoinArgs {
+  const float* scale_a; const float* shift_a; const float* cs_a; int act_a;
+  const float* scale_b; const float* shift_b; const float* cs_b; int act_b;
+  float eps;
+  int has_norm;
+  int M, Ka, Kb;
+};
+
+__global__ void __launch_bounds__(kT16Threads, 1)
+gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmWah,
+                   const __grid_constant__ CUtensorMap tmWal, const __grid_constant__ CUtensorMap tmXb,
+                   const __grid_constant__ CUtensorMap tmWbh, const __grid_constant__ CUtensorMap tmWbl,
+                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmYn,
+                   const JoinArgs a) {
+  using Cfg = JoinCfg;
+  constexpr int S = kJStages;
+  constexpr int BN = kJBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* out_stage = smem + S * Cfg::kStageBytes;
+  float* params = reinterpret_cast<float*>(out_stage + kTcStageOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);
+  uint64_t* full = bars;
+  uint64_t* conv = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tmem_full = bars + 3 * S;       // [2] both accumulators of a tile ready
+  uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] drained (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb_a = (a.Ka + kTcBK - 1) / kTcBK, nkb_b = (a.Kb + kTcBK - 1) / kTcBK;
+  const int nkb = nkb_a + nkb_b;
+  const int num_mt = (a.M + kTcBM - 1) / kTcBM;
+
+  auto stage_raw = [&](int s) { return smem + s * Cfg::kStageBytes; };
+  auto stage_ah = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes; };
+  auto stage_al = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + Cfg::kABytes; };
+  auto stage_bh = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes; };
+  auto stage_bl = [&](int s) {
+    return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes + Cfg::kBBytes;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          const bool second = kb >= nkb_a;
+          const int k0 = (second ? kb - nkb_a : kb) * kTcBK;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], Cfg::kRawBytes + 2 * Cfg::kBBytes);
+          tma_load_2d(stage_raw(s), second ? &tmXb : &tmXa, k0, mt * kTcBM, &full[s]);
+          tma_load_2d(stage_bh(s), second ? &tmWbh : &tmWah, k0, 0, &full[s]);
+          tma_load_2d(stage_bl(s), second ? &tmWbl : &tmWal, k0, 0, &full[s]);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+      uint32_t it = 0, tile = 0;
+      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
+        const uint32_t par = tile & 1, aph = (tile >> 1) & 1;
+        mbar_wait(&tmem_empty[par], aph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          const bool second = kb >= nkb_a;
+          const uint32_t tmem_d = tmem_base + (par * 2 + (second ? 1 : 0)) * BN;
+          const bool first_slab = second ? (kb == nkb_a) : (kb == 0);
+          mbar_wait(&conv[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t a_h = umma_desc_sw64(smem_u32(stage_ah(s)));
+          const uint64_t a_l = umma_desc_sw64(smem_u32(stage_al(s)));
+          const uint64_t b_h = umma_desc_sw64(smem_u32(stage_bh(s)));
+          const uint64_t b_l = umma_desc_sw64(smem_u32(stage_bl(s)));
+#pragma unroll
+          for (int k = 0; k < kTcBK / 16; ++k) {
+            const uint64_t off = (uint64_t)(k * 16 * 2) >> 4;
+            umma_f16(tmem_d, a_l + off, b_h + off, idesc, (first_slab && k == 0) ? 0u : 1u);
+            umma_f16(tmem_d, a_h + off, b_l + off, idesc, 1u);
+            umma_f16(tmem_d, a_h + off, b_h + off, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[par]);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ fp32 -> (xh, xl) fp16 split
+    const int t = threadIdx.x - 64;
+    const int c = t & 3;
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        const uint8_t* raw = stage_raw(s);
+        uint8_t* ah = stage_ah(s);
+        uint8_t* al = stage_al(s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (t >> 2) + 32 * i;
+          const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
+          uint4 hi, lo;
+          split8(v0, v1, hi, lo);
+          const uint32_t off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(ah + off) = hi;
+          *reinterpret_cast<uint4*>(al + off) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&conv[s]);
+      }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 6..9)
+    const int q = warp & 3;
+    const int et = threadIdx.x - 192;    // 0..127 == output column for the parameter load
+    uint8_t* my_stage = out_stage + (warp - 6) * 4096;
+    uint32_t tile = 0;
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++tile) {
+      const uint32_t par = tile & 1, aph = (tile >> 1) & 1;
+      float* prm = params + par * 4 * BN;
+      prm[et] = (a.scale_a ? __ldg(a.scale_a + et) : 1.f) * __ldg(a.cs_a + et);
+      prm[BN + et] = a.shift_a ? __ldg(a.shift_a + et) : 0.f;
+      prm[2 * BN + et] = (a.scale_b ? __ldg(a.scale_b + et) : 1.f) * __ldg(a.cs_b + et);
+      prm[3 * BN + et] = a.shift_b ? __ldg(a.shift_b + et) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[par], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t0 = tmem_base + (par * 2) * BN + ((uint32_t)(q * 32) << 16);
+      float ss = 0.f, inv = 0.f;
+      const int passes = a.has_norm ? 2 : 1;
+#pragma unroll 1
+      for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t ra[32], rb[32];
+          DH3D_TMEM_LD_32X32(ra, t0 + (uint32_t)c0);
+          DH3D_TMEM_LD_32X32(rb, t0 + (uint32_t)(BN + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (pass == passes - 1 && c0 + 32 >= BN) {  // both accumulators fully read for the last time
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[par]);
+          }
+          // activation chosen once per chunk, outside the element loops: the per-element runtime switch of
+          // tc_act made this epilogue ~2000 instructions per chunk (instruction-cache misses, 0.36 ms per step)
+          float v[32], u[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = fmaf(__uint_as_float(ra[j]), prm[c0 + j], prm[BN + c0 + j]);
+            u[j] = fmaf(__uint_as_float(rb[j]), prm[2 * BN + c0 + j], prm[3 * BN + c0 + j]);
+          }
+          if (a.act_a == DH3D_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (a.act_a != DH3D_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], a.act_a);
+          }
+          if (a.act_b == DH3D_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u[j] = fmaxf(u[j], 0.f);
+          } else if (a.act_b != DH3D_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u[j] = tc_act(u[j], a.act_b);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+          if (pass == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= inv;
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(pass == 0 ? &tmY : &tmYn, my_stage, c0, mt * kTcBM + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        inv = rsqrtf(fmaxf(ss, a.eps));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // params[par] are rewritten two tiles later
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// packed_a / packed_b: linear_prepack16 buffers of Wa [Ka,128] / Wb [Kb,128]; yn may be null (no normalised copy)
+int linear_join_tc16_launch(const float* xa, int ldxa, const void* packed_a, const float* scale_a,
+                            const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_b,
+                            const float* scale_b, const float* shift_b, int act_b, float* y, int ldy, float* yn,
+                            int ldn, float eps, int M, int Ka, int Kb, int N, cudaStream_t st) {
+  if (N != kJBN) return DH3D_ERR_UNSUPPORTED;
+  int rc = t16_check(xa, ldxa, packed_a, M, Ka, N);
+  if (rc != DH3D_OK) return rc;
+  if ((rc = t16_check(xb, ldxb, packed_b, M, Kb, N)) != DH3D_OK) return rc;
+  if (!y) return DH3D_ERR_NULL;
+  if (ldy % 4 || ldy < N || (yn && (ldn % 4 || ldn < N))) return DH3D_ERR_DIM;
+  if ((((uintptr_t)y | (uintptr_t)yn | (uintptr_t)scale_a | (uintptr_t)shift_a | (uintptr_t)scale_b |
+        (uintptr_t)shift_b) & 15) != 0)
+    return DH3D_ERR_ALIGN;
+  const T16Packed pa = t16_unpack(packed_a, Ka, N), pb = t16_unpack(packed_b, Kb, N);
+  CUtensorMap mxa, mah, mal, mxb, mbh, mbl, my, myn;
+  if ((rc = make_map(&mxa, xa, M, Ka, ldxa, kTcBM)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&mah, pa.wh, N, t16_kp(Ka), t16_kp(Ka), kJBN)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&mal, pa.wl, N, t16_kp(Ka), t16_kp(Ka), kJBN)) != DH3D_OK) return rc;
+  if ((rc = make_map(&mxb, xb, M, Kb, ldxb, kTcBM)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&mbh, pb.wh, N, t16_kp(Kb), t16_kp(Kb), kJBN)) != DH3D_OK) return rc;
+  if ((rc = make_map_f16(&mbl, pb.wl, N, t16_kp(Kb), t16_kp(Kb), kJBN)) != DH3D_OK) return rc;
+  if ((rc = make_map(&my, y, M, N, ldy, 32)) != DH3D_OK) return rc;
+  if (yn) { if ((rc = make_map(&myn, yn, M, N, ldn, 32)) != DH3D_OK) return rc; }
+  else myn = my;
+  JoinArgs a{scale_a, shift_a, pa.cs, act_a, scale_b, shift_b, pb.cs, act_b, eps, yn ? 1 : 0, M, Ka, Kb};
+  cudaError_t e = cudaFuncSetAttribute(gemm_join16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)JoinCfg::kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  const int num_mt = ceil_div(M, kTcBM);
+  const int grid = num_mt < num_sms() ? num_mt : num_sms();
+  gemm_join16_kernel<<<grid, kT16Threads, JoinCfg::kSmemBytes, st>>>(mxa, mah, mal, mxb, mbh, mbl, my, myn, a);
+  return launch_status();
+}
+
 }  // namespace dh3d

@@ -240,6 +240,27 @@ def add_l2_normalize_rows(a, b, eps):
     return s, y
 
 
+def linear_join(xa, packed_a, scale_a, shift_a, act_a, xb, packed_b, scale_b, shift_b, act_b, eps=None):
+    """act_a((xa @ Wa)*scale_a + shift_a) + act_b((xb @ Wb)*scale_b + shift_b), and with ``eps`` also its
+    l2-normalised rows, in one launch (weights as linear_prepack buffers; N must be 128).
+    Returns y, or (y, y_normalised) when eps is given."""
+    M, Ka = _rows(xa)
+    Mb, Kb = _rows(xb)
+    (Kpa, N), (Kpb, Nb) = packed_a._dh3d_kn, packed_b._dh3d_kn
+    if M != Mb or Kpa != Ka or Kpb != Kb or N != Nb:
+        raise _lib.Dh3dError("linear_join: shape mismatch")
+    y = torch.empty(xa.shape[:-1] + (N,), dtype=f32, device=xa.device)
+    yn = torch.empty_like(y) if eps is not None else None
+    _lib.stats.tag = "M%d_K%d+%d_N%d" % (M, Ka, Kb, N)
+    call("dh3d_linear_join_packed", check(xa, f32, "xa"), Ka, ctypes.c_void_p(packed_a.data_ptr()),
+         opt(scale_a, f32, "scale_a"), opt(shift_a, f32, "shift_a"), int(act_a), check(xb, f32, "xb"), Kb,
+         ctypes.c_void_p(packed_b.data_ptr()), opt(scale_b, f32, "scale_b"), opt(shift_b, f32, "shift_b"),
+         int(act_b), check(y, f32, "y"), N, opt(yn, f32, "yn"), N, _cf(float(eps or 0.0)), M, Ka, Kb, N,
+         stream_ptr(xa.device))
+    _lib.stats.tag = None
+    return (y, yn) if eps is not None else y
+
+
 def _rows(x):
     """[..., C] contiguous tensor -> (M, C) row view parameters."""
     C = x.shape[-1]

@@ -198,6 +198,18 @@ DH3D_API int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, c
 DH3D_API int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                               const float* shift, int act, const float* w2, float b2, int act2,
                               float* y, int M, int K, int N, void* stream);
+/* Two-branch join of backbone_local_dilate (core/backbones.py:121-123) with the descriptor normalisation of
+ * core/model.py:177-181 in one launch:
+ *     y  = act_a((xa @ Wa)*scale_a + shift_a) + act_b((xb @ Wb)*scale_b + shift_b)          [M,N]
+ *     yn = y / sqrt(max(sum_n y^2, eps))      (y_normalized may be NULL)
+ * packed_wa / packed_wb come from dh3d_linear_prepack (fp16-pair layout, the default).  N must be 128 (the row
+ * norm needs the whole output row in one tile); otherwise, or with DH3D_GEMM_SPLIT=tf32, DH3D_ERR_UNSUPPORTED and
+ * the caller composes dh3d_linear_packed x2 + dh3d_add_l2_normalize_rows. */
+DH3D_API int dh3d_linear_join_packed(const float* xa, int ldxa, const void* packed_wa, const float* scale_a,
+                            const float* shift_a, int act_a, const float* xb, int ldxb,
+                            const void* packed_wb, const float* scale_b, const float* shift_b, int act_b,
+                            float* y, int ldy, float* y_normalized, int ldn, float eps, int M, int Ka,
+                            int Kb, int N, void* stream);
 DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream);
 DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);

@@ -102,3 +102,35 @@ def test_tf32_split_path_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
                         "vs_fp64 or rowdot or strided"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("M,Ka,Kb", [(1000, 192, 64), (128 * 149 + 5, 192, 64), (300, 64, 32), (4096, 36, 192)])
+def test_linear_join_vs_fp64_and_unfused(M, Ka, Kb):
+    """dh3d_linear_join_packed: relu(BN(xa@Wa)) + relu(BN(xb@Wb)) and its l2-normalised rows in one launch
+    (core/backbones.py:121-123 + core/model.py:177-181) against fp64 and against the separate launches."""
+    import os
+    from dh3d_b200 import ops
+    if os.environ.get("DH3D_GEMM_SPLIT") == "tf32":
+        pytest.skip("the join kernel exists for the fp16-pair layout only (callers compose the separate ops)")
+    rng = np.random.RandomState(M + Ka)
+    N = 128
+    xa, xb = rng.randn(M, Ka).astype(np.float32), rng.randn(M, Kb).astype(np.float32)
+    wa, wb = (rng.randn(Ka, N) / np.sqrt(Ka)).astype(np.float32), (rng.randn(Kb, N) / np.sqrt(Kb)).astype(np.float32)
+    sa, sb = (rng.rand(N) + 0.5).astype(np.float32), (rng.rand(N) + 0.5).astype(np.float32)
+    ba, bb = rng.randn(N).astype(np.float32) * 0.3, rng.randn(N).astype(np.float32) * 0.3
+    ba, bb = ba.astype(np.float32), bb.astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    pa, pb = ops.linear_prepack(t(wa)), ops.linear_prepack(t(wb))
+    y, yn = ops.linear_join(t(xa), pa, t(sa), t(ba), 1, t(xb), pb, t(sb), t(bb), 1, eps=1e-8)
+    want = (np.maximum(xa.astype(np.float64) @ wa * sa + ba, 0) + np.maximum(xb.astype(np.float64) @ wb * sb + bb, 0))
+    scale = np.sqrt(np.mean(want ** 2))
+    assert np.abs(y.cpu().numpy() - want).max() <= 1e-4 * scale + 1e-4 * np.abs(want).max()
+    wn = want / np.sqrt(np.maximum((want ** 2).sum(-1, keepdims=True), 1e-8))
+    assert np.abs(yn.cpu().numpy() - wn).max() <= 2e-5
+    # the unfused composition gives the same sum up to the epilogue's rounding, and the same normalisation of it
+    u = ops.linear(t(xa), t(wa), scale=t(sa), shift=t(ba), act=1, packed=pa) + \
+        ops.linear(t(xb), t(wb), scale=t(sb), shift=t(bb), act=1, packed=pb)
+    assert (y - u).abs().max().item() <= 1e-5 * scale
+    assert (yn - ops.l2_normalize_rows(y, 1e-8)).abs().max().item() <= 1e-6
+    only = ops.linear_join(t(xa), pa, t(sa), t(ba), 1, t(xb), pb, t(sb), t(bb), 1)
+    assert torch.equal(only, y)

@@ -474,8 +474,8 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
           if (nt * BN + c0e < a.Dout) {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = tc_act(fmaf(__uint_as_float(rg[j]), prm[c0e + j], prm[BN + c0e + j]), a.act);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rg[j]), prm[c0e + j], prm[BN + c0e + j]);
+            tc_act32(v, a.act);
 #pragma unroll
             for (int pass = 0; pass < 32 / OR; ++pass) {
               if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -296,8 +296,8 @@ flexconv_tc_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_const
           if (nt * BN + c0 < a.Dout) {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = tc_act(fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]), a.act);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]);
+            tc_act32(v, a.act);
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
 #pragma unroll

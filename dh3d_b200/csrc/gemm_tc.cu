@@ -246,8 +246,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = tc_act(fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]), ep.act);
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]);
+          tc_act32(v, ep.act);
           if constexpr (ROWDOT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dot = fmaf(v[j], prm[2 * BN + c0 + j], dot);

@@ -285,8 +285,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = tc_act(fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]), ep.act);
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), prm[c0 + j], prm[BN + c0 + j]);
+          tc_act32(v, ep.act);
           if constexpr (ROWDOT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) dot = fmaf(v[j], prm[2 * BN + c0 + j], dot);
@@ -705,20 +705,8 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
             v[j] = fmaf(__uint_as_float(ra[j]), prm[c0 + j], prm[BN + c0 + j]);
             u[j] = fmaf(__uint_as_float(rb[j]), prm[2 * BN + c0 + j], prm[3 * BN + c0 + j]);
           }
-          if (a.act_a == DH3D_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (a.act_a != DH3D_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], a.act_a);
-          }
-          if (a.act_b == DH3D_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) u[j] = fmaxf(u[j], 0.f);
-          } else if (a.act_b != DH3D_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) u[j] = tc_act(u[j], a.act_b);
-          }
+          tc_act32(v, a.act_a);
+          tc_act32(u, a.act_b);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += u[j];
           if (pass == 0) {

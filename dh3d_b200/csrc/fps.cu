@@ -64,9 +64,9 @@ fps_reg_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restr
     const int tk = tid * PPT + i;
     const int k = (tk % V) * 512 + tk / V;
     const bool valid = (tk < 512 * V) && (k < n);
-    px[i] = valid ? s_xyz[k * 3 + 0] : 0.f;
-    py[i] = valid ? s_xyz[k * 3 + 1] : 0.f;
-    pz[i] = valid ? s_xyz[k * 3 + 2] : 0.f;
+    px[i] = valid ? __ldg(ds + k * 3 + 0) : 0.f;
+    py[i] = valid ? __ldg(ds + k * 3 + 1) : 0.f;
+    pz[i] = valid ? __ldg(ds + k * 3 + 2) : 0.f;
     td[i] = valid ? 1e38f : -1.f;  // -1 pins d2 = min(d,-1) = -1, which never beats best = -1
   }
 
@@ -134,8 +134,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 template <int PPT>
 __global__ void __launch_bounds__(kFpsClusterThreads, 1)
-fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restrict__ idxs) {
-  extern __shared__ __align__(16) float s_xyz[];  // n*3 floats (each CTA keeps the whole cloud)
+fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restrict__ idxs, int xyz_in_smem) {
+  // xyz_in_smem: each CTA keeps the whole cloud (n*3 floats, 96 KB at n = 8192) to read the coordinates of the
+  // point chosen in the previous round; otherwise they are read through L1 (__ldg) and the CTA needs no dynamic
+  // shared memory, so it can share an SM with the ~200 KB persistent kernels of the main stream (DH3D_FPS_XYZ)
+  extern __shared__ __align__(16) float s_xyz[];
   __shared__ __align__(8) unsigned long long s_slot[2][kFpsClusterSlots];
 
   const uint32_t rank = cluster_ctarank();
@@ -145,7 +148,8 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = (int)rank * kFpsClusterThreads + tid;  // thread id within the cloud
 
-  for (int j = tid; j < n * 3; j += kFpsClusterThreads) s_xyz[j] = ds[j];
+  if (xyz_in_smem)
+    for (int j = tid; j < n * 3; j += kFpsClusterThreads) s_xyz[j] = ds[j];
   if (tid < 2 * kFpsClusterSlots) (&s_slot[0][0])[tid] = 0ull;  // tag 0 = no round
   __syncthreads();
   cluster_sync_all();  // every CTA's slots are initialised before any remote store lands
@@ -158,9 +162,9 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __r
     const int tk = g * PPT + i;
     const int k = (tk % V) * 512 + tk / V;
     const bool valid = (tk < 512 * V) && (k < n);
-    px[i] = valid ? s_xyz[k * 3 + 0] : 0.f;
-    py[i] = valid ? s_xyz[k * 3 + 1] : 0.f;
-    pz[i] = valid ? s_xyz[k * 3 + 2] : 0.f;
+    px[i] = valid ? __ldg(ds + k * 3 + 0) : 0.f;
+    py[i] = valid ? __ldg(ds + k * 3 + 1) : 0.f;
+    pz[i] = valid ? __ldg(ds + k * 3 + 2) : 0.f;
     td[i] = valid ? 1e38f : -1.f;
   }
 
@@ -173,7 +177,12 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __r
   int old = 0;
   if (g == 0) out[0] = 0;
   for (int j = 1; j < m; ++j) {
-    const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+    float x1, y1, z1;
+    if (xyz_in_smem) {
+      x1 = s_xyz[old * 3 + 0]; y1 = s_xyz[old * 3 + 1]; z1 = s_xyz[old * 3 + 2];
+    } else {
+      x1 = __ldg(ds + old * 3 + 0); y1 = __ldg(ds + old * 3 + 1); z1 = __ldg(ds + old * 3 + 2);
+    }
     float best = -1.f;
     int bslot = 0;
 #pragma unroll
@@ -264,7 +273,9 @@ static int fps_launch_reg(int b, int n, int m, const float* inp, int32_t* out, c
 
 template <int PPT>
 static int fps_launch_cluster(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
-  size_t smem = (size_t)n * 3 * sizeof(float);
+  static const bool xyz_global = getenv("DH3D_FPS_XYZ") && getenv("DH3D_FPS_XYZ")[0] == 'g';
+  const int xyz_in_smem = xyz_global ? 0 : 1;
+  size_t smem = xyz_in_smem ? (size_t)n * 3 * sizeof(float) : 0;
   cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -280,7 +291,7 @@ static int fps_launch_cluster(int b, int n, int m, const float* inp, int32_t* ou
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT>, n, m, inp, out);
+  e = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT>, n, m, inp, out, xyz_in_smem);
   if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
   return launch_status();
 }

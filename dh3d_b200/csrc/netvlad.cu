@@ -22,7 +22,7 @@ constexpr int kVK = 64;     // clusters
 constexpr int kVTP = 32;    // points per sub-tile
 constexpr int kVXS = kVD + 4;  // padded row stride of the x tile (floats)
 constexpr int kVMaxSlabs = 32; // upper bound of CTAs (slabs of points) per cloud
-constexpr int kVSlice = 128;   // rows of hidden1_weights per projection CTA
+constexpr int kVSlice = 64;    // rows of hidden1_weights per projection CTA (256 CTAs: two per SM hide the weight-load latency)
 
 struct __align__(16) VladSmem {
   float w[kVD][kVK];        // cluster_weights           64 KB
@@ -191,7 +191,7 @@ netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restric
         make_float4(v[k] * s_inv[k], v[k + 1] * s_inv[k + 1], v[k + 2] * s_inv[k + 2], v[k + 3] * s_inv[k + 3]);
 }
 
-// split-K projection: CTA s handles rows [s*128, s*128+128) of hidden1_weights [16384, 256] for a
+// split-K projection: CTA s handles rows [s*64, s*64+64) of hidden1_weights [16384, 256] for a
 // group of up to 32 clouds; thread = output column.  part_h [slices][B][256].
 __global__ void __launch_bounds__(kVD)
 netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__ hw, int B, int KD,
@@ -210,7 +210,7 @@ netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
-#pragma unroll 2
+#pragma unroll 4
   for (int r = 0; r < kVSlice; r += 4) {   // one broadcast LDS.128 feeds four FMAs (was one LDS per FMA)
     const float w0 = __ldg(w + (long long)r * kVD), w1 = __ldg(w + (long long)(r + 1) * kVD),
                 w2 = __ldg(w + (long long)(r + 2) * kVD), w3 = __ldg(w + (long long)(r + 3) * kVD);

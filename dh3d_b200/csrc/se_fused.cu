@@ -48,14 +48,14 @@ se_pool_excite_kernel(const float* __restrict__ x, const int32_t* __restrict__ n
   const int grp0 = lane & ~(LP - 1);      // first lane of this point's lane group
   const int sub = lane / LP;              // point of the warp iteration
 
-  float w1r[Cfg::kW1Reg ? 4 : 1][Cfg::kW1Reg ? H : 1];
+  unsigned long long w1r[Cfg::kW1Reg ? 4 : 1][Cfg::kW1Reg ? H / 2 : 1];   // W1[4q+i][2j], [2j+1] packed
   if constexpr (Cfg::kW1Reg) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < H; j += 4) {
-        const float4 t = ldg4(w1 + (4 * q + i) * H + j);
-        w1r[i][j] = t.x; w1r[i][j + 1] = t.y; w1r[i][j + 2] = t.z; w1r[i][j + 3] = t.w;
+        const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2*>(w1 + (4 * q + i) * H + j));
+        w1r[i][j / 2] = t.x; w1r[i][j / 2 + 1] = t.y;
       }
   }
   const float bias1 = __ldg(b1 + q);
@@ -66,6 +66,7 @@ se_pool_excite_kernel(const float* __restrict__ x, const int32_t* __restrict__ n
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool k8 = (K == 8);
+  const int nshift = (n & (n - 1)) == 0 ? __ffs(n) - 1 : -1;   // power-of-two clouds: no integer division per point
 
   int4 ia = make_int4(0, 0, 0, 0), ib = ia;   // neighbour ids of the NEXT iteration (K == 8 only)
   auto row_of = [&](int g) { const int r = g * PP + sub; return r < rows ? r : rows - 1; };
@@ -76,7 +77,7 @@ se_pool_excite_kernel(const float* __restrict__ x, const int32_t* __restrict__ n
   for (int g = warp0; g < groups; g += nwarps) {
     const int r = row_of(g);
     const bool valid = g * PP + sub < rows;
-    const int cloud0 = (r / n) * n;
+    const int cloud0 = nshift >= 0 ? ((r >> nshift) << nshift) : (r / n) * n;
     const float* fb = x + (long long)cloud0 * C + 4 * q;
     float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
     const float4 xv = ldg4(x + (long long)r * C + 4 * q);
@@ -106,29 +107,31 @@ se_pool_excite_kernel(const float* __restrict__ x, const int32_t* __restrict__ n
         if (best.w < t.w) best.w = t.w;
       }
     }
-    // hidden partial sums over this lane's 4 pooled channels
-    float part[H];
+    // hidden partial sums over this lane's 4 pooled channels (packed fp32x2 FMAs: two hidden units per instruction)
+    unsigned long long part2[H / 2];
     const float pv[4] = {best.x, best.y, best.z, best.w};
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) part2[j] = 0ull;
     if constexpr (Cfg::kW1Reg) {
 #pragma unroll
-      for (int j = 0; j < H; ++j) part[j] = pv[0] * w1r[0][j];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 1; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < H; ++j) part[j] = fmaf(pv[i], w1r[i][j], part[j]);
+        for (int j = 0; j < H / 2; ++j) ffma2(part2[j], w1r[i][j], pv[i]);
     } else {
-#pragma unroll
-      for (int j = 0; j < H; ++j) part[j] = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < H; j += 4) {
-          const float4 t = reinterpret_cast<const float4*>(s_w1)[(i * (H / 4) + j / 4) * LP + q];
-          part[j] = fmaf(pv[i], t.x, part[j]);
-          part[j + 1] = fmaf(pv[i], t.y, part[j + 1]);
-          part[j + 2] = fmaf(pv[i], t.z, part[j + 2]);
-          part[j + 3] = fmaf(pv[i], t.w, part[j + 3]);
+          const ulonglong2 t = reinterpret_cast<const ulonglong2*>(s_w1)[(i * (H / 4) + j / 4) * LP + q];
+          ffma2(part2[j / 2], t.x, pv[i]);
+          ffma2(part2[j / 2 + 1], t.y, pv[i]);
         }
+    }
+    float part[H];
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j) {
+      const float2 t = unpack2(part2[j]);
+      part[2 * j] = t.x; part[2 * j + 1] = t.y;
     }
     // reduce-scatter across the lane group: after the last step lane q holds the full sum of hidden unit q
 #pragma unroll
@@ -142,19 +145,22 @@ se_pool_excite_kernel(const float* __restrict__ x, const int32_t* __restrict__ n
       }
     }
     const float h = fmaxf(part[0] + bias1, 0.f);
-    float4 acc = bias2;
+    unsigned long long acc01, acc23;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc01) : "f"(bias2.x), "f"(bias2.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc23) : "f"(bias2.z), "f"(bias2.w));
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       const float hj = __shfl_sync(0xffffffffu, h, grp0 | j);
-      const float4 t = *reinterpret_cast<const float4*>(s_w2 + j * C + 4 * q);
-      acc.x = fmaf(hj, t.x, acc.x); acc.y = fmaf(hj, t.y, acc.y);
-      acc.z = fmaf(hj, t.z, acc.z); acc.w = fmaf(hj, t.w, acc.w);
+      const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(s_w2 + j * C + 4 * q);
+      ffma2(acc01, t.x, hj);
+      ffma2(acc23, t.y, hj);
     }
-    float4 o;
-    o.x = fmaxf(xv.x + xv.x * (1.f / (1.f + __expf(-acc.x))), 0.f);
-    o.y = fmaxf(xv.y + xv.y * (1.f / (1.f + __expf(-acc.y))), 0.f);
-    o.z = fmaxf(xv.z + xv.z * (1.f / (1.f + __expf(-acc.z))), 0.f);
-    o.w = fmaxf(xv.w + xv.w * (1.f / (1.f + __expf(-acc.w))), 0.f);
+    const float2 a01 = unpack2(acc01), a23 = unpack2(acc23);
+    float4 o;   // sigmoid with the fast reciprocal (2 ulp): the gate feeds a 1e-4 feature tolerance
+    o.x = fmaxf(xv.x + xv.x * __fdividef(1.f, 1.f + __expf(-a01.x)), 0.f);
+    o.y = fmaxf(xv.y + xv.y * __fdividef(1.f, 1.f + __expf(-a01.y)), 0.f);
+    o.z = fmaxf(xv.z + xv.z * __fdividef(1.f, 1.f + __expf(-a23.x)), 0.f);
+    o.w = fmaxf(xv.w + xv.w * __fdividef(1.f, 1.f + __expf(-a23.y)), 0.f);
     if (valid) *reinterpret_cast<float4*>(out + (long long)r * C + 4 * q) = o;
   }
 }

@@ -157,9 +157,12 @@ def algorithmic(tag, name):
     if name == "dh3d_linear_rowdot_packed":   # hidden [M,N] never written: x + W + one float per row
         M, K, N = d["M"], d["K"], d["N"]
         return 4.0 * (M * K + K * N + N + M), 2.0 * M * K * N + 2.0 * M * N
-    if name == "dh3d_flex_conv_pm":
+    if name in ("dh3d_flex_conv_pm", "dh3d_flex_conv_pm_packed"):
         n, K, Ci, Co = d["n"], d["K"], d["Ci"], d["Co"]
         return 4.0 * (n * Ci + n * Co + n * K + 3 * n + 4 * Ci * Co), 8.0 * n * K * Ci + 8.0 * n * Ci * Co
+    if name == "dh3d_linear_join_packed":   # both inputs and weights once, y and its normalised copy once
+        M, Ka, Kb, N = d["M"], d["Ka"], d["Kb"], d["N"]
+        return 4.0 * (M * (Ka + Kb) + (Ka + Kb) * N + 2 * M * N), 2.0 * M * (Ka + Kb) * N
     if name == "dh3d_knn_bruteforce_pm":
         B, N, K = d["B"], d["N"], d["K"]
         return B * (12.0 * N + 8.0 * N * K), 8.0 * B * N * N
@@ -180,6 +183,9 @@ OP_KERNEL = {
     "dh3d_knn_bruteforce_pm": ("knn_query_kernel<8, 1, 1",),
     "dh3d_farthest_point_sample": ("fps_cluster_kernel", "fps_reg_kernel"),
     "dh3d_flex_conv_pm": ("flexconv_ca_kernel", "flexconv_tc_kernel"),
+    "dh3d_flex_conv_pm_packed": ("flexconv_ca_kernel", "flexconv_tc_kernel"),
+    "dh3d_linear_join_packed": ("gemm_join16_kernel",),
+    "dh3d_se_pool_excite": ("se_pool_excite_kernel",),
 }
 
 

@@ -251,7 +251,7 @@ def linear_join(xa, packed_a, scale_a, shift_a, act_a, xb, packed_b, scale_b, sh
         raise _lib.Dh3dError("linear_join: shape mismatch")
     y = torch.empty(xa.shape[:-1] + (N,), dtype=f32, device=xa.device)
     yn = torch.empty_like(y) if eps is not None else None
-    _lib.stats.tag = "M%d_K%d+%d_N%d" % (M, Ka, Kb, N)
+    _lib.stats.tag = "M%d_Ka%d_Kb%d_N%d" % (M, Ka, Kb, N)
     call("dh3d_linear_join_packed", check(xa, f32, "xa"), Ka, ctypes.c_void_p(packed_a.data_ptr()),
          opt(scale_a, f32, "scale_a"), opt(shift_a, f32, "shift_a"), int(act_a), check(xb, f32, "xb"), Kb,
          ctypes.c_void_p(packed_b.data_ptr()), opt(scale_b, f32, "scale_b"), opt(shift_b, f32, "shift_b"),

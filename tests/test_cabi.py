@@ -61,6 +61,27 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.dh3d_three_interpolate_grad(1, 8, 4, 2, one, one, null, one, null) == -1
     assert lib.dh3d_keypoint_nms(one, one, 1, 40, 0.5, 0.01, 16, 1, one, one, one, 1 << 30, null) == -3   # N < 50
     assert lib.dh3d_keypoint_nms(one, one, 1, 400, 0.5, 0.01, 16, 1, one, one, one, 16, null) == -4
+    # fused inference entry points: squeeze/excite, prepacked FlexConv, two-branch join
+    f = ctypes.c_float
+    assert lib.dh3d_se_pool_excite(null, one, one, one, one, one, one, 1, 8, 4, 64, 16, null) == -1
+    assert lib.dh3d_se_pool_excite(one, one, one, one, one, one, one, 1, 0, 4, 64, 16, null) == -2
+    assert lib.dh3d_se_pool_excite(one, one, one, one, one, one, one, 1, 8, 4, 96, 24, null) == -3      # C not 64/128
+    assert lib.dh3d_se_pool_excite(one, one, one, one, one, one, one, 1, 8, 4, 64, 32, null) == -3      # H != C/4
+    assert lib.dh3d_flex_conv_prepack_bytes(64, 128) >= 2 * 4 * 64 * 128 * 4 + 128 * 4
+    assert lib.dh3d_flex_conv_prepack(null, one, null, null, null, 64, 128, one, null) == -1
+    assert lib.dh3d_flex_conv_prepack(one, one, null, null, null, 6, 128, ctypes.c_void_p(256), null) == -3
+    assert lib.dh3d_flex_conv_prepack(one, one, null, null, null, 64, 128, ctypes.c_void_p(16), null) == -5  # alignment
+    assert lib.dh3d_flex_conv_pm_packed(one, null, one, one, one, 1, 8, 4, 64, 64, null, 0, one, 1 << 30, null) == -1
+    assert lib.dh3d_flex_conv_pm_packed(one, ctypes.c_void_p(256), one, one, one, 1, 8, 65, 64, 64, null, 0, one,
+                                        1 << 30, null) == -3                                             # K > 64
+    assert lib.dh3d_flex_conv_pm_packed(one, ctypes.c_void_p(256), one, one, one, 1, 8, 4, 64, 64, null, 0, one, 0,
+                                        null) == -4
+    assert lib.dh3d_linear_join_packed(one, 192, one, null, null, 1, one, 64, one, null, null, 1, one, 64, null, 64,
+                                       f(1e-8), 8, 192, 64, 64, null) == -3                             # N != 128
+    assert lib.dh3d_linear_join_packed(one, 192, one, null, null, 1, null, 64, one, null, null, 1, one, 128, null,
+                                       128, f(1e-8), 8, 192, 64, 128, null) == -1
+    assert lib.dh3d_linear_join_packed(one, 190, one, null, null, 1, one, 64, one, null, null, 1, one, 128, null,
+                                       128, f(1e-8), 8, 190, 64, 128, null) == -2                       # K % 4
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 128, 64, 256) == 0                      # unsupported dims
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 256, 64, 256) > 0
 

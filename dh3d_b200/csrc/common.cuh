@@ -72,6 +72,26 @@ __device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long lon
 __device__ __forceinline__ void fadd2(unsigned long long& acc, unsigned long long f) {
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(f));
 }
+__device__ __forceinline__ unsigned long long fsub2s(unsigned long long a, float s) {   // {a.x - s, a.y - s}
+  unsigned long long r;
+  asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nsub.rn.f32x2 %0, %1, t;\n}" : "=l"(r) : "l"(a), "f"(s));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ffma2v(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ float2 unpack2(unsigned long long v) {
   float2 r;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));

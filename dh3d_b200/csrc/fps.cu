@@ -168,6 +168,16 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __r
     td[i] = valid ? 1e38f : -1.f;
   }
 
+  unsigned long long qx[PPT >= 2 ? PPT / 2 : 1], qy[PPT >= 2 ? PPT / 2 : 1], qz[PPT >= 2 ? PPT / 2 : 1];
+  if constexpr (PPT >= 2) {
+#pragma unroll
+    for (int i = 0; i < PPT / 2; ++i) {
+      qx[i] = pack2(px[2 * i], px[2 * i + 1]);
+      qy[i] = pack2(py[2 * i], py[2 * i + 1]);
+      qz[i] = pack2(pz[2 * i], pz[2 * i + 1]);
+    }
+  }
+
   // lane r < 4 sends to CTA r; slot index = global warp id
   const uint32_t slot0 = smem_u32(&s_slot[0][0]);
   const uint32_t my_slot_off = (uint32_t)((int)rank * kFpsClusterWarps + warp) * 8u;
@@ -185,13 +195,29 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __r
     }
     float best = -1.f;
     int bslot = 0;
+    if constexpr (PPT >= 2) {
+      // two points per instruction (sm_100 FADD2 / FMUL2 / FFMA2): same IEEE operations in the same order as
+      // the scalar form below, 6 instead of 12 FP instructions per pair -- the rounds of this kernel share the
+      // SM's issue slots with the k-NN scan of the main stream
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-      const float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
-      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-      const float d2 = fminf(d, td[i]);
-      td[i] = d2;
-      if (d2 > best) { best = d2; bslot = i; }
+      for (int i = 0; i < PPT / 2; ++i) {
+        const unsigned long long dx = fsub2s(qx[i], x1), dy = fsub2s(qy[i], y1), dz = fsub2s(qz[i], z1);
+        const float2 d = unpack2(ffma2v(dz, dz, ffma2v(dx, dx, fmul2(dy, dy))));
+        const float da = fminf(d.x, td[2 * i]), db = fminf(d.y, td[2 * i + 1]);
+        td[2 * i] = da;
+        td[2 * i + 1] = db;
+        if (da > best) { best = da; bslot = 2 * i; }
+        if (db > best) { best = db; bslot = 2 * i + 1; }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PPT; ++i) {
+        const float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
+        const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        const float d2 = fminf(d, td[i]);
+        td[i] = d2;
+        if (d2 > best) { best = d2; bslot = i; }
+      }
     }
     const int bits = __float_as_int(best);
     const int wmax = __reduce_max_sync(0xffffffffu, bits);

@@ -284,6 +284,12 @@ struct KnnMetric {      // knn_bruteforce_kernel_gpu.cu.cc:102-107 (nvcc-contrac
   static __device__ __forceinline__ float d2(float dx, float dy, float dz) {
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
   }
+  // two candidates per instruction (FMUL2 / FFMA2): the same operations in the same order, lane by lane
+  static constexpr bool kPacked = true;
+  static __device__ __forceinline__ unsigned long long d2v(unsigned long long dx, unsigned long long dy,
+                                                           unsigned long long dz) {
+    return ffma2v(dz, dz, ffma2v(dy, dy, fmul2(dx, dx)));
+  }
   static __device__ __forceinline__ float key(float d) { return __fsqrt_rn(d); }
   // every d2 with sqrt.rn(d2) <= k satisfies d2 <= k^2*(1+2^-23) < the bound below
   static __device__ __forceinline__ float bound(float k) { return __fmul_rn(__fmul_rn(k, k), 1.000001f); }
@@ -298,6 +304,9 @@ struct ThreeNnMetric {  // tf_interpolate.cpp:60-103: un-fused (dx*dx + dy*dy) +
   static __device__ __forceinline__ float d2(float dx, float dy, float dz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
   }
+  // no packed form: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (seen in SASS; 3-NN indices changed),
+  // and this metric is defined by its UN-fused roundings -- the scalar __fmul_rn / __fadd_rn path is used
+  static constexpr bool kPacked = false;
   static __device__ __forceinline__ float key(float d) { return d; }
   static __device__ __forceinline__ float bound(float k) { return k; }
   static __device__ __forceinline__ int rank_of(int x, int, int, int) { return x; }
@@ -471,19 +480,38 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
       }
       // one coalesced 512-byte load per chunk, staged in the warp's shared-memory slot and read back as LDS.128
       // broadcasts
+      // The staged chunk is pair-interleaved -- slot 2P = (x0,x1,y0,y1), slot 2P+1 = (z0,z1,w0,w1) of candidates
+      // 2P, 2P+1 -- so two broadcast LDS.128 feed packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): 6 instead of
+      // 12 FP instructions per candidate pair, bit-identical distances.  Lane pairs swap halves with one shuffle
+      // pair so that every lane still writes one 16-byte slot.
       const float4 mine = __ldg(cloud + c * kKnnChunk + lane);
+      const bool odd = lane & 1;
+      const float s0v = __shfl_xor_sync(0xffffffffu, odd ? mine.x : mine.z, 1);
+      const float s1v = __shfl_xor_sync(0xffffffffu, odd ? mine.y : mine.w, 1);
       __syncwarp();
-      s_chunk[tid >> 5][lane] = mine;
+      s_chunk[tid >> 5][lane] = odd ? make_float4(s0v, mine.z, s1v, mine.w) : make_float4(mine.x, s0v, mine.y, s1v);
       __syncwarp();
-      const float4* cand = s_chunk[tid >> 5];
+      const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(s_chunk[tid >> 5]);
 #pragma unroll
       for (int j0 = 0; j0 < kKnnChunk; j0 += 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 v = cand[j0 + u];
-          const float d2 = M::d2(v.x - qx, v.y - qy, v.z - qz);
-          if (d2 <= thr2) {
-            s_buf[cnt][tid] = make_float2(d2, v.w);
+        for (int u = 0; u < 8; u += 2) {
+          const ulonglong2 xy = cand[j0 + u], zw = cand[j0 + u + 1];
+          float2 d2;
+          if constexpr (M::kPacked) {
+            d2 = unpack2(M::d2v(fsub2s(xy.x, qx), fsub2s(xy.y, qy), fsub2s(zw.x, qz)));
+          } else {
+            const float2 x = unpack2(xy.x), yv = unpack2(xy.y), z = unpack2(zw.x);
+            d2.x = M::d2(x.x - qx, yv.x - qy, z.x - qz);
+            d2.y = M::d2(x.y - qx, yv.y - qy, z.y - qz);
+          }
+          const float2 w = unpack2(zw.y);
+          if (d2.x <= thr2) {
+            s_buf[cnt][tid] = make_float2(d2.x, w.x);
+            ++cnt;
+          }
+          if (d2.y <= thr2) {
+            s_buf[cnt][tid] = make_float2(d2.y, w.y);
             ++cnt;
           }
         }

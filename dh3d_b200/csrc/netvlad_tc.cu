@@ -609,7 +609,7 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int q = warp & 3;                 // TMEM lane quadrant
     const bool owner = lane < 16;           // M = 64 accumulator: rows 16q .. 16q+15 sit in lanes 0..15
     const int row = 16 * q + (lane & 15);
-    float mys[4] = {0.f, 0.f, 0.f, 0.f};    // S[k] partials of this warp, k = 16j + (lane & 15)
+    float mys[4] = {0.f, 0.f, 0.f, 0.f};    // S[k] partials of this warp, k = 4 * lane + j (lanes 0..15)
     for (int f = 0; f < a.subslabs; ++f) {
       const int i0 = f * kNFlush, i1 = min(ntiles, i0 + kNFlush);
       for (int i = i0; i < i1; ++i) {
@@ -643,13 +643,9 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint32_t col = ((row >> 3) << 4), sub = (row & 7) * 2;   // 16-byte chunk (8 points), byte inside it
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
-          const float av = p[k] * scale;          // in [0, 1]
-          float sv = owner ? av : 0.f;
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-          if ((k & 15) == (lane & 15)) mys[k >> 4] += sv;
+          p[k] *= scale;                          // assignment in [0, 1]; 0 in the non-owner lanes (scale = 0)
           if (owner) {
-            const float as = av * kAScale;
+            const float as = p[k] * kAScale;
             const __half h = __float2half_rn(as);
             const __half l = __float2half_rn(as - __half2float(h));
             const uint32_t off = k * 128 + ((((col >> 4) ^ (k & 7))) << 4) + sub;
@@ -659,6 +655,21 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         fence_proxy_async();
         mbar_arrive(a_full);
+        // S[k] += sum over the 16 rows of this warp: reduce-scatter over lanes 0..15 (60 shuffles instead of the 256
+        // of a per-cluster butterfly); lane L ends with the sums of clusters 4L .. 4L+3
+#pragma unroll
+        for (int sft = 32; sft >= 4; sft >>= 1) {
+          const int bit = sft >> 2;               // lane bit 8, 4, 2, 1
+          const bool up = (lane & bit) != 0;
+#pragma unroll
+          for (int t = 0; t < sft; ++t) {
+            const float send = up ? p[t] : p[t + sft];
+            const float keep = up ? p[t + sft] : p[t];
+            p[t] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mys[j] += p[j];
       }
       // ---- flush the sub-slab: V (TMEM, all 128 lanes) -> part_v, S -> part_s
       const int pidx = c * a.subslabs + f;
@@ -690,7 +701,7 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       if (owner) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s_sum[q * 64 + 16 * j + lane] = mys[j]; mys[j] = 0.f; }
+        for (int j = 0; j < 4; ++j) { s_sum[q * 64 + 4 * lane + j] = mys[j]; mys[j] = 0.f; }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 192;

@@ -607,9 +607,12 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else if (warp < 10) {
     // ------------------------------------------------------------------ softmax + flush (128 threads)
     const int q = warp & 3;                 // TMEM lane quadrant
-    const bool owner = lane < 16;           // M = 64 accumulator: rows 16q .. 16q+15 sit in lanes 0..15
+    // M = 64 accumulator: rows 16q .. 16q+15 sit in lanes 0..15 of the quadrant.  Lane L + 16 takes clusters 32..63
+    // of row L (its copy of the upper 32 logits arrives by shuffle), so all 32 lanes share the exp / convert / store
+    // work of the stage that paces the kernel.
+    const int hsel = lane >> 4, kb = hsel * 32;
     const int row = 16 * q + (lane & 15);
-    float mys[4] = {0.f, 0.f, 0.f, 0.f};    // S[k] partials of this warp, k = 4 * lane + j (lanes 0..15)
+    float mys[2] = {0.f, 0.f};              // S[k] partials of this warp, k = kb + 2 * (lane & 15) + j
     for (int f = 0; f < a.subslabs; ++f) {
       const int i0 = f * kNFlush, i1 = min(ntiles, i0 + kNFlush);
       for (int i = i0; i < i1; ++i) {
@@ -622,44 +625,45 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(l_free);                 // the logits of the next tile may overwrite the accumulator now
-        float p[64];
+        float p[32];
         float mx = -CUDART_INF_F;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          p[k] = fmaf(__uint_as_float(r0[k]), s_prm[k], s_prm[64 + k]);
-          p[32 + k] = fmaf(__uint_as_float(r1[k]), s_prm[32 + k], s_prm[96 + k]);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, hsel ? r0[k] : r1[k], 16);
+          const uint32_t mine = hsel ? other : r0[k];
+          p[k] = fmaf(__uint_as_float(mine), s_prm[kb + k], s_prm[64 + kb + k]);
+          mx = fmaxf(mx, p[k]);
         }
-#pragma unroll
-        for (int k = 0; k < 64; ++k) mx = fmaxf(mx, p[k]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
         float sum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) { p[k] = __expf(p[k] - mx); sum += p[k]; }
+        for (int k = 0; k < 32; ++k) { p[k] = __expf(p[k] - mx); sum += p[k]; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
         const int n = (t_begin + i) * kNT + row;
         float scale = 0.f;
-        if (owner && n < a.N) scale = __ldg(a.att + (long long)b * a.N + n) / sum;
+        if (n < a.N) scale = __ldg(a.att + (long long)b * a.N + n) / sum;
         if (i > 0) mbar_wait(a_free, (i - 1) & 1);   // the residual product of the previous tile has read the tile
-        uint8_t* pah = smem + NvSmem2::ah;
-        uint8_t* pal = smem + NvSmem2::al;
+        // assignment tile: B operand [64 k rows x 64 points], K-major, 128B swizzle: element (k, row)
+        uint8_t* pah = smem + NvSmem2::ah + kb * 128;
+        uint8_t* pal = smem + NvSmem2::al + kb * 128;
         const uint32_t col = ((row >> 3) << 4), sub = (row & 7) * 2;   // 16-byte chunk (8 points), byte inside it
 #pragma unroll
-        for (int k = 0; k < 64; ++k) {
-          p[k] *= scale;                          // assignment in [0, 1]; 0 in the non-owner lanes (scale = 0)
-          if (owner) {
-            const float as = p[k] * kAScale;
-            const __half h = __float2half_rn(as);
-            const __half l = __float2half_rn(as - __half2float(h));
-            const uint32_t off = k * 128 + ((((col >> 4) ^ (k & 7))) << 4) + sub;
-            *reinterpret_cast<__half*>(pah + off) = h;
-            *reinterpret_cast<__half*>(pal + off) = l;
-          }
+        for (int k = 0; k < 32; ++k) {
+          p[k] *= scale;                          // assignment in [0, 1]
+          const float as = p[k] * kAScale;
+          const __half h = __float2half_rn(as);
+          const __half l = __float2half_rn(as - __half2float(h));
+          const uint32_t off = k * 128 + ((((col >> 4) ^ (k & 7))) << 4) + sub;   // (kb + k) & 7 == k & 7
+          *reinterpret_cast<__half*>(pah + off) = h;
+          *reinterpret_cast<__half*>(pal + off) = l;
         }
         fence_proxy_async();
         mbar_arrive(a_full);
-        // S[k] += sum over the 16 rows of this warp: reduce-scatter over lanes 0..15 (60 shuffles instead of the 256
-        // of a per-cluster butterfly); lane L ends with the sums of clusters 4L .. 4L+3
+        // S[k] += sum over the 16 rows of this warp: reduce-scatter over lane bits 3..0 (30 shuffles); lane L ends
+        // with the sums of clusters kb + 2 (L & 15), +1
 #pragma unroll
-        for (int sft = 32; sft >= 4; sft >>= 1) {
-          const int bit = sft >> 2;               // lane bit 8, 4, 2, 1
+        for (int sft = 16; sft >= 2; sft >>= 1) {
+          const int bit = sft >> 1;               // lane bit 8, 4, 2, 1
           const bool up = (lane & bit) != 0;
 #pragma unroll
           for (int t = 0; t < sft; ++t) {
@@ -668,8 +672,8 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             p[t] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mys[j] += p[j];
+        mys[0] += p[0];
+        mys[1] += p[1];
       }
       // ---- flush the sub-slab: V (TMEM, all 128 lanes) -> part_v, S -> part_s
       const int pidx = c * a.subslabs + f;
@@ -699,10 +703,8 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int e = threadIdx.x - 192; e < kND * kNK / 4; e += 128)
           reinterpret_cast<float4*>(pv)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (owner) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s_sum[q * 64 + 4 * lane + j] = mys[j]; mys[j] = 0.f; }
-      }
+      for (int j = 0; j < 2; ++j) { s_sum[q * 64 + kb + 2 * (lane & 15) + j] = mys[j]; mys[j] = 0.f; }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 192;
       if (e < 64)

@@ -485,6 +485,10 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int i = 0; i < ntiles; ++i) {
         const int bb = i & 1, n = i >> 1;
         const int row0 = b * a.N + (t_begin + i) * kNT;
+        // the buffer of tile i+1 frees late (two tile buffers), so its HBM latency is taken now, into L2: the load
+        // issued after the wait below then only pays the L2 -> shared-memory leg
+        if (i + 1 < ntiles)
+          for (int s = 0; s < 8; ++s) tma_prefetch_2d(&tmX, s * 32, row0 + kNT);
         mbar_wait(&x_free[bb], (uint32_t)(n & 1) ^ 1u);   // the tile that used this buffer two tiles ago is consumed
         mbar_arrive_expect_tx(&raw_full[bb], 8 * kRawSlab);
         for (int s = 0; s < 8; ++s)

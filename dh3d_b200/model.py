@@ -92,7 +92,7 @@ class DH3D(nn.Module):
 
 
 class GraphedForward(object):
-    """The forward pass captured once into a CUDA graph (all ~50 kernel launches, both streams) and
+    """The forward pass captured once into a CUDA graph (all ~32 kernel launches, both streams) and
     replayed per batch: removes the host launch cost and the inter-kernel gaps.  Shapes are frozen to
     the example batch; outputs are static tensors that the next replay overwrites."""
 

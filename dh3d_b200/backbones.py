@@ -25,8 +25,9 @@ from torch import nn
 
 from . import ops
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
-from .layers import (SLIM_BN_EPS, BatchNorm, Conv1x1, ConvolutionPointset, FlexConvolution,
-                     FlexPooling)
+from ._lib import Dh3dError
+from .layers import (SLIM_BN_EPS, BatchNorm, Conv1x1, ConvolutionPointset, Flex_Avg, FlexConvolution,
+                     FlexPooling, FoldedModule, default_store)
 
 
 class DilateGeometry(object):
@@ -86,15 +87,19 @@ class SEBlock(nn.Module):
 class FlexConvDilate(nn.Module):
     def __init__(self, cin, outdims, dilate, knn=8, concat=True, add_se="max_pool", upsample=True):
         super().__init__()
-        assert add_se in ("max_pool", "")
-        self.dilate, self.knn, self.upsample = dilate, knn, upsample
+        if add_se not in ("max_pool", "avg_pool", "", None):
+            raise Dh3dError("flex_conv_dilate: add_se must be 'max_pool', 'avg_pool' or '' (got %r)" % (add_se,))
+        self.dilate, self.knn, self.upsample, self.add_se = dilate, knn, upsample, add_se or ""
         self.outdims = list(outdims)
         c = cin
         for i, d in enumerate(outdims):
             setattr(self, "flexconv_%d" % i, FlexConvolution(c, d))
             setattr(self, "flexconv_%d_bn" % i, BatchNorm(d))
             c = d
-        self.se = SEBlock(c) if add_se == "max_pool" else None
+        self.se = SEBlock(c) if self.add_se else None
+        # add_se='avg_pool' (core/backbones.py:79-82): x_pool = flex_avg(x, ...) * (1/knn); 'se_avgpool' owns a
+        # zero, non-trainable position_theta variable
+        self.se_avgpool = Flex_Avg(c) if self.add_se == "avg_pool" else None
         self.concat_conv1d = FeatureConv1d(c + cin, c) if concat else None
 
     def forward(self, xyz, feat, knn_indices=None, geometry=None, cat=None, defer_concat=False):
@@ -120,7 +125,13 @@ class FlexConvDilate(nn.Module):
         for i in range(len(self.outdims)):
             x = getattr(self, "flexconv_%d" % i).forward_pm(
                 x, pts, nbr, bn=getattr(self, "flexconv_%d_bn" % i), act=ACT_RELU)
-        if self.se is not None:
+        if self.se_avgpool is not None:
+            # the 1/knn scaling rides in the FlexConv epilogue (scale = 1/knn, no shift)
+            inv_k = torch.full((x.shape[2],), 1.0 / self.knn, dtype=x.dtype, device=x.device)
+            pooled = ops.flex_conv(x, self.se_avgpool.position_theta, self.se_avgpool.position_bias, nbr, pts,
+                                   scale=inv_k, shift=torch.zeros_like(inv_k))
+            x = self.se(x, pooled)
+        elif self.se is not None:
             y = self.se.forward_fused(x, nbr)
             x = y if y is not None else self.se(x, ops.flex_pool(x, nbr))
         if self.upsample and self.dilate > 1:
@@ -138,18 +149,20 @@ class FlexConvDilate(nn.Module):
 
 
 class LocalBackbone(nn.Module):
-    """backbone_local_dilate (featdim == 128: no final_fc)."""
+    """backbone_local_dilate (core/backbones.py:104-127); featdim < 128 appends 'final_fc' (:125-126)."""
 
-    def __init__(self, init_feat_dim=32, featdim=128, dilate2=8, knn=8):
+    def __init__(self, init_feat_dim=32, featdim=128, dilate2=8, knn=8, add_se="max_pool"):
         super().__init__()
-        assert featdim == 128, "featdim < 128 (final_fc) is not part of the shipped configs"
-        self.knn = knn
+        if not 0 < featdim <= 128:
+            raise Dh3dError("backbone_local_dilate: featdim must be in 1..128 (got %d)" % featdim)
+        self.knn, self.featdim = knn, featdim
         self.initconv = ConvolutionPointset(3, init_feat_dim)
         self.initconv_bn = BatchNorm(init_feat_dim)
-        self.stage1 = FlexConvDilate(init_feat_dim, [64, 64], dilate=1, knn=knn, concat=False)
+        self.stage1 = FlexConvDilate(init_feat_dim, [64, 64], dilate=1, knn=knn, concat=False, add_se=add_se)
         self.before_stage2_conv1d = FeatureConv1d(64, 64)
-        self.stage2 = FlexConvDilate(64, [128, 128], dilate=dilate2, knn=knn, concat=True)
+        self.stage2 = FlexConvDilate(64, [128, 128], dilate=dilate2, knn=knn, concat=True, add_se=add_se)
         self.local_stage1_shortcut = FeatureConv1d(64, 128)
+        self.final_fc = FeatureConv1d(128, featdim) if featdim < 128 else None
 
     def forward(self, points, knn_ind, geometry=None, with_desc=False):
         """-> feat [B,N,128]; with_desc=True: (feat, l2-normalised feat) from one fused pass (model.py:177-181)."""
@@ -168,18 +181,21 @@ class LocalBackbone(nn.Module):
         fused = (pa is not None and pb is not None and la.W.shape[3] == 128 and
                  not os.environ.get("DH3D_GEMM_SPLIT", "f16").lower().startswith("t") and
                  not os.environ.get("DH3D_JOIN", "fused").lower().startswith("s"))
+        want_desc = with_desc and self.final_fc is None
         if fused:
             cat = self.stage2(points, None, geometry=geometry, cat=cat, defer_concat=True)
-            return ops.linear_join(cat, pa, sa, ba, la.act, x1, pb, sb, bb, lb.act,
-                                   eps=1e-8 if with_desc else None)
-        x2 = self.stage2(points, None, geometry=geometry, cat=cat)
-        sc = self.local_stage1_shortcut(x1)
-        if with_desc:
-            return ops.add_l2_normalize_rows(sc, x2, 1e-8)
-        return ops.add(sc, x2)
+            y = ops.linear_join(cat, pa, sa, ba, la.act, x1, pb, sb, bb, lb.act, eps=1e-8 if want_desc else None)
+        else:
+            x2 = self.stage2(points, None, geometry=geometry, cat=cat)
+            sc = self.local_stage1_shortcut(x1)
+            y = ops.add_l2_normalize_rows(sc, x2, 1e-8) if want_desc else ops.add(sc, x2)
+        if self.final_fc is None:
+            return y
+        y = self.final_fc(y)   # featdim < 128 (core/backbones.py:125-126): Conv2D + BN + ReLU, then the l2 norm
+        return (y, ops.l2_normalize_rows(y, 1e-8)) if with_desc else y
 
 
-class AttentionHead(nn.Module):
+class AttentionHead(FoldedModule):
     """1x1 stack -> 1 logit -> sigmoid.  detection_block: 128->128->256->1024->1;
     globalatt_block: 256->1024->1."""
 
@@ -217,7 +233,7 @@ class GlobalAttBlock(AttentionHead):
         super().__init__(cin, (256, 1024) if cin > 256 else (1024,))
 
 
-class GlobalNetVLADBlock(nn.Module):
+class GlobalNetVLADBlock(FoldedModule):
     """global_netvald_block(xyz, features, att, is_training, cluster_size=64, output_dim=256,
     add_batch_norm=True, gating=True) -- variables live at the root scope in the checkpoint."""
 
@@ -242,7 +258,17 @@ class GlobalNetVLADBlock(nn.Module):
                            self.gating_weights, gbn, final_l2norm=final_l2norm)
 
 
-def global_netvald_block(block, xyz, features, att, is_training=False, **unused):
-    """Function form with the reference's argument order (core/backbones.py:202)."""
-    assert not is_training, "inference only"
+def global_netvald_block(xyz, features, att, is_training=False, cluster_size=64, output_dim=256, add_batch_norm=True,
+                         gating=True, store=None, scope="netvlad", **unused_kwargs):
+    """core/backbones.py:202-279, same argument order: xyz [B,N,3] (unused by the reference too), features
+    [B,N,D], att [B,N,1] -> 'final_global' [B,output_dim] (NOT l2-normalised; core/model.py:205 does that).
+    The variables (cluster_weights, cluster_weights2, cluster_bn, hidden1_weights, bn, gating_weights, gating_bn)
+    live in ``store[scope]``.  Inference only; the shipped add_batch_norm=True / gating=True form only."""
+    if is_training:
+        raise Dh3dError("global_netvald_block: inference only (is_training must be False)")
+    if not add_batch_norm or not gating:
+        raise Dh3dError("global_netvald_block: only add_batch_norm=True, gating=True (the shipped configuration) is built")
+    D = features.shape[2]
+    block = (store if store is not None else default_store).layer(
+        scope, lambda: GlobalNetVLADBlock(D, cluster_size, output_dim).to(features.device))
     return block(xyz, features, att, final_l2norm=False)

@@ -17,6 +17,8 @@ class DH3DConfig:
     gl_dims: List[int] = field(default_factory=lambda: [256])
     cluster_size: int = 64       # global_netvald_block defaults
     output_dim: int = 256
+    add_se: str = "max_pool"     # flex_conv_dilate's squeeze/excite pooling: 'max_pool' | 'avg_pool' | ''
+    global_subsample: int = -1   # > 0: FPS-subsample the global-branch features before attention / NetVLAD
 
     @property
     def input_knn_indices(self):

@@ -32,6 +32,22 @@ TENSORPACK_BN_EPS = 1e-5  # tensorpack BatchNorm default epsilon (library defaul
 SLIM_BN_EPS = 1e-3        # tf.contrib slim / layers batch_norm default epsilon
 
 
+class FoldedModule(nn.Module):
+    """Base of every layer that caches weight-derived operands in ``self._folded`` (folded BatchNorm, prepacked
+    tensor-core weights, scalars read back to the host).  The cache is keyed on nothing but the parameters'
+    current values and device, so everything that can change either drops it: ``.to()/.cuda()/.float()``
+    (``_apply``), ``load_state_dict`` (``_load_from_state_dict``) and ``invalidate_folded`` for in-place edits."""
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._folded = None
+        return out
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._folded = None
+
+
 class BatchNorm(nn.Module):
     """Inference BatchNorm statistics.  tensorpack names: gamma, beta, mean/EMA, variance/EMA;
     slim names: gamma, beta, moving_mean, moving_variance -- both map to these four tensors."""
@@ -53,10 +69,43 @@ class BatchNorm(nn.Module):
 
 
 def invalidate_folded(module):
-    """Drop every cached folded-BN tensor (call after changing parameters)."""
+    """Drop every cached weight-derived operand (call after editing parameters in place; device moves and
+    ``load_state_dict`` do it themselves, see FoldedModule)."""
     for m in module.modules():
         if hasattr(m, "_folded"):
             m._folded = None
+        if hasattr(m, "_side"):
+            m._side = None
+
+
+class VariableStore(nn.ModuleDict):
+    """What a TF variable scope is to the reference's function forms (``layer.apply`` under
+    ``tf.variable_scope``): the layer a function form creates is kept under its ``name`` and re-used by later
+    calls with the same name, so its parameters can be filled by a checkpoint loader and moved with ``.cuda()``."""
+
+    def layer(self, name, factory):
+        if name is None:
+            raise ValueError("the function forms need name= (the reference's variable scope) to own parameters")
+        key = name.replace(".", "/")
+        if key not in self:
+            self[key] = factory()
+        return self[key]
+
+
+default_store = VariableStore()
+
+
+def _activation(y, activation):
+    """Keras ``activations.get``: None / 'linear' / callable / 'relu' / 'sigmoid'."""
+    if activation is None or activation == "linear":
+        return y
+    if callable(activation):
+        return activation(y)
+    if activation == "relu":
+        return torch.relu(y)
+    if activation == "sigmoid":
+        return torch.sigmoid(y)
+    raise ValueError("unsupported activation %r" % (activation,))
 
 
 class KnnBruteforce(nn.Module):
@@ -87,7 +136,7 @@ def flex_pooling(features, neighborhoods, data_format="simple", name=None):
     return FlexPooling()(features, neighborhoods)
 
 
-class FlexConvolution(nn.Module):
+class FlexConvolution(FoldedModule):
     def __init__(self, in_channels, filters, use_feature_bias=True, dp=3):
         super().__init__()
         self.filters = int(filters)
@@ -122,21 +171,54 @@ class FlexConvolution(nn.Module):
                              feature_bias=fb, scale=scale, shift=shift, act=act)
 
 
-def flex_convolution(layer, features, positions, neighborhoods):
-    return layer(features, positions, neighborhoods)
+def flex_convolution(features, positions, neighborhoods, filters, activation=None, kernel_initializer=None,
+                     position_bias_initializer=None, features_bias_initializer=None, use_feature_bias=True,
+                     data_format="simple", trainable=True, name=None, store=None):
+    """core/layers.py:439-461, same argument order: features [B,Din,N], positions [B,Dp,N], neighborhoods
+    [B,K,N] i32 -> activation(flexconv + feature_bias) [B,filters,N].  The layer (position_theta [Dp,Din,filters],
+    position_bias [Din,filters], feature_bias [filters,1]) lives in ``store`` under ``name``; a new layer starts
+    with Glorot-uniform theta and zero biases like the reference's default initialisers (``kernel_initializer``
+    may be a callable ``f(tensor)`` applied in place instead)."""
+    assert data_format == "simple", "only data_format='simple' (rank-3 tensors) is built"
+
+    def make():
+        Din, Dp = features.shape[1], positions.shape[1]
+        layer = FlexConvolution(Din, filters, use_feature_bias=use_feature_bias, dp=Dp)
+        with torch.no_grad():
+            if callable(kernel_initializer):
+                kernel_initializer(layer.position_theta)
+            else:
+                nn.init.xavier_uniform_(layer.position_theta)
+        return layer.to(features.device)
+
+    layer = (store if store is not None else default_store).layer(name, make)
+    return _activation(layer(features, positions, neighborhoods), activation)
 
 
 class Flex_Avg(FlexConvolution):
-    """FlexConv with theta = 0 and bias = I: the plain neighbour SUM (caller scales by 1/K,
-    core/backbones.py:80-83).  Requires Din == Dout."""
+    """core/layers.py:342-436: FlexConv with position_theta = 0 (a non-trainable VARIABLE, so it is in the
+    checkpoint) and position_bias = eye(Dout) (a constant, not a variable): the plain neighbour SUM; the
+    caller scales by 1/K (core/backbones.py:80-83).  Requires Din == Dout like the reference's tf.eye(Dout)."""
 
-    def __init__(self, channels):
-        super().__init__(channels, channels, use_feature_bias=False)
-        with torch.no_grad():
-            self.position_bias.copy_(torch.eye(channels))
+    def __init__(self, channels, dp=3):
+        super().__init__(channels, channels, use_feature_bias=False, dp=dp)
+        del self.position_bias
+        self.register_buffer("position_bias", torch.eye(channels), persistent=False)
 
 
-class ConvolutionPointset(nn.Module):
+def flex_avg(features, positions, neighborhoods, filters, activation=None, kernel_initializer=None,
+             data_format="simple", trainable=True, name=None, store=None):
+    """core/layers.py:464-480, same argument order -> neighbour sum [B,filters,N] (filters must equal Din)."""
+    assert data_format == "simple"
+    if int(filters) != features.shape[1]:
+        raise ValueError("flex_avg: filters (%d) must equal the input channels (%d): position_bias is eye(filters)"
+                         % (filters, features.shape[1]))
+    layer = (store if store is not None else default_store).layer(
+        name, lambda: Flex_Avg(int(filters), dp=positions.shape[1]).to(features.device))
+    return _activation(layer(features, positions, neighborhoods), activation)
+
+
+class ConvolutionPointset(FoldedModule):
     def __init__(self, in_channels, filters, use_feature_bias=False):
         super().__init__()
         self.filters = int(filters)
@@ -164,7 +246,27 @@ class ConvolutionPointset(nn.Module):
                                  scale=scale, shift=shift, act=act)
 
 
-class Conv1x1(nn.Module):
+def convolution_pointset(features, neighborhoods, filters, activation=None, kernel_initializer=None,
+                         position_bias_initializer=None, features_bias_initializer=None, use_feature_bias=False,
+                         data_format="simple", trainable=True, name=None, store=None):
+    """core/layers.py:686-707, same argument order: features [B,Din,N], neighborhoods [B,K,N] ->
+    activation(conv_pointset (+ feature_bias)) [B,filters,N]; parameters owned by ``store[name]``."""
+    assert data_format == "simple"
+
+    def make():
+        layer = ConvolutionPointset(features.shape[1], filters, use_feature_bias=use_feature_bias)
+        with torch.no_grad():
+            if callable(kernel_initializer):
+                kernel_initializer(layer.position_theta)
+            else:
+                nn.init.xavier_uniform_(layer.position_theta)
+        return layer.to(features.device)
+
+    layer = (store if store is not None else default_store).layer(name, make)
+    return _activation(layer(features, neighborhoods), activation)
+
+
+class Conv1x1(FoldedModule):
     """tensorpack ``Conv2D(kernel_shape=1)`` on [B,N,1,C] (core/tf_utils.py:99-109): W [1,1,Cin,Cout],
     b [Cout], optional BatchNorm ('bn' scope) and activation.  Point-major only."""
 

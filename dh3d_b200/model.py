@@ -12,22 +12,34 @@ import torch
 from torch import nn
 
 from . import ops
+from ._lib import Dh3dError
 from .backbones import (DetectionBlock, DilateGeometry, FlexConvDilate, GlobalAttBlock,
-                        GlobalNetVLADBlock, LocalBackbone)
+                        GlobalNetVLADBlock, LocalBackbone, subsample)
 from .configs import DH3DConfig
 from .layers import invalidate_folded
 
 
 class DH3D(nn.Module):
-    def __init__(self, config=None):
+    """``separate_global_backbone=True`` gives the global branch its OWN copy of backbone_local_dilate
+    (``global_local.*``): the reference ships two separately trained networks (models/local, models/global)
+    whose backbone weights differ, so reproducing both in one pass needs both backbones.  The default (one
+    shared backbone) is BASELINE.json configs[2] and what a jointly trained checkpoint would use."""
+
+    def __init__(self, config=None, separate_global_backbone=False):
         super().__init__()
         self.config = config or DH3DConfig()
         c = self.config
-        self.local = LocalBackbone(c.init_feat_dim, c.featdim, dilate2=c.dilate, knn=c.knn_num)
+        self.local = LocalBackbone(c.init_feat_dim, c.featdim, dilate2=c.dilate, knn=c.knn_num, add_se=c.add_se)
         if c.detection:
             self.detection_block_reliable = DetectionBlock(c.featdim)
         if c.extract_global:
-            assert list(c.gl_dims) == [256], "only the shipped gl_dims=[256] configuration is built"
+            if c.gl_dims[-1] != 256 or c.cluster_size != 64 or c.output_dim != 256:
+                raise Dh3dError("DH3D: the NetVLAD kernels are built for gl_dims[-1] == 256, cluster_size == 64, "
+                                "output_dim == 256 (the shipped global_config); got gl_dims=%s cluster_size=%d "
+                                "output_dim=%d" % (list(c.gl_dims), c.cluster_size, c.output_dim))
+            if separate_global_backbone:
+                self.global_local = LocalBackbone(c.init_feat_dim, c.featdim, dilate2=c.dilate, knn=c.knn_num,
+                                                  add_se=c.add_se)
             self.global_before_assemble = FlexConvDilate(c.featdim, c.gl_dims, dilate=c.gl_dilate,
                                                          knn=c.knn_num, concat=False, add_se="")
             self.globalatt = GlobalAttBlock(c.gl_dims[-1])
@@ -36,6 +48,11 @@ class DH3D(nn.Module):
 
     def invalidate(self):
         invalidate_folded(self)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._side = None   # the side stream belongs to the device the parameters were on
+        return out
 
     @torch.no_grad()
     def forward(self, points, knn_inds=None, outputs=("local_desc", "attention", "globaldesc"),
@@ -53,7 +70,7 @@ class DH3D(nn.Module):
         # xyz-only geometry (FPS chain is latency-bound and independent of stage 1): side stream
         geometry = None
         if overlap:
-            if self._side is None:
+            if self._side is None or self._side.device != points.device:
                 self._side = torch.cuda.Stream(device=points.device)
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
@@ -81,9 +98,15 @@ class DH3D(nn.Module):
             # (running the detector head on the side stream next to the global branch was measured: no gain,
             #  3.18 vs 3.17 ms per step -- every large kernel here is a persistent one-CTA-per-SM grid)
             g = geometry if same_geometry else None
-            forglobal = self.global_before_assemble(points, feat, geometry=g)
+            gfeat = feat
+            if getattr(self, "global_local", None) is not None:
+                gfeat = self.global_local(points, knn_inds, geometry=geometry)
+            forglobal = self.global_before_assemble(points, gfeat, geometry=g)
+            gpoints = points
+            if c.global_subsample > 0:   # core/model.py:118-121
+                gpoints, forglobal, _ = subsample(points, forglobal, c.global_subsample)
             att = self.globalatt(forglobal)
-            out["globaldesc"] = self.netvlad(points, forglobal, att, final_l2norm=True)
+            out["globaldesc"] = self.netvlad(gpoints, forglobal, att, final_l2norm=True)
         if "xyz_feat" in want:
             out["xyz_feat"] = torch.cat([points, out["local_desc"]], dim=-1)
         if "xyz_feat_att" in want and c.detection:
@@ -127,6 +150,9 @@ def init_random_(model, seed=0, knn=8, offset_scale=2.0):
         for name, p in model.named_parameters():
             shape = tuple(p.shape)
             leaf = name.split(".")[-1]
+            if "se_avgpool" in name:    # Flex_Avg: zero, non-trainable theta (core/layers.py:380-385)
+                p.zero_()
+                continue
             r = lambda: torch.randn(shape, generator=g)
             if leaf == "gamma":
                 v = 1.0 + 0.1 * r()

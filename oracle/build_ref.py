@@ -13,6 +13,9 @@ infrastructure only -- see oracle/__init__.py.
                        55-153 are extracted at BUILD time into oracle/_ref/; that file also holds
                        TF op registrations that cannot compile without TensorFlow), g++ -O2, no -mfma
                        like tf_interpolate_compile.sh:11-15.
+  dh3d_weights.npz     the MODEL VARIABLES of the two shipped checkpoints (models/{local,global}; optimizer
+                       slots dropped), keys 'local:<tf name>' / 'global:<tf name>': data, not source -- lets the
+                       real-weight parity tests run on the GPU box, where /root/reference does not exist.
 The reference's own build system (cmake + FindTensorFlow) is not run: TensorFlow is absent.
 The k-NN CPU functor needs Eigen (absent) and is not built.
 """
@@ -99,6 +102,36 @@ def build_cpu(force=False):
     return CPU_SO
 
 
+WEIGHTS_NPZ = os.path.join(OUT, "dh3d_weights.npz")
+
+
+def stage_weights(force=False):
+    if os.path.exists(WEIGHTS_NPZ) and not force:
+        return WEIGHTS_NPZ
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(HERE))
+    from dh3d_b200.checkpoint import read_tensor_bundle
+    out = {}
+    for tag in ("local", "global"):
+        for k, v in read_tensor_bundle(os.path.join(REF, "models", tag, tag + "model")).items():
+            if "Adam" in k or k.startswith(("EMA/", "beta")) or k in ("global_step", "learning_rate"):
+                continue
+            out["%s:%s" % (tag, k)] = np.asarray(v)
+    np.savez(WEIGHTS_NPZ, **out)
+    return WEIGHTS_NPZ
+
+
+def load_staged_weights():
+    """-> ({tf_name: ndarray} local, {tf_name: ndarray} global) or None when not staged."""
+    if not os.path.exists(WEIGHTS_NPZ):
+        return None
+    import numpy as np
+    z = np.load(WEIGHTS_NPZ)
+    loc = {k[6:]: z[k] for k in z.files if k.startswith("local:")}
+    glo = {k[7:]: z[k] for k in z.files if k.startswith("global:")}
+    return loc, glo
+
+
 def build(force=False, verbose=False):
     """No-op (returns None) when /root/reference is absent, e.g. on the GPU box."""
     if not os.path.isdir(os.path.join(REF, "user_ops", "kernels")):
@@ -107,6 +140,8 @@ def build(force=False, verbose=False):
         return None
     os.makedirs(OUT, exist_ok=True)
     a, b = build_cuda(force), build_cpu(force)
+    if os.path.isdir(os.path.join(REF, "models", "global")):
+        stage_weights(force)
     if verbose:
         print("built", a, "and", b)
     return a, b

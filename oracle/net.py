@@ -90,6 +90,15 @@ def knn_pm(xyz_pm, k):
     return ids  # [B,N,K]
 
 
+def flex_avg_pm(feat_pm, xyz_pm, nbr_pm, p, prefix):
+    """Flex_Avg (core/layers.py:342-436): FlexConv with the stored (zero) theta and bias = eye -> neighbour sum."""
+    C = feat_pm.shape[2]
+    out = oracle.flex_convolution(np.transpose(feat_pm, (0, 2, 1)), np.transpose(xyz_pm, (0, 2, 1)),
+                                  np.transpose(nbr_pm, (0, 2, 1)), p[prefix + ".position_theta"],
+                                  np.eye(C, dtype=np.float32), centre_is_self=True, f64=not _MODE["reference_cpu"])
+    return np.transpose(out.astype(np.float64), (0, 2, 1))
+
+
 def flex_conv_dilate(xyz, feat, p, prefix, dilate, outdims, knn=8, knn_indices=None, concat=True,
                      add_se=True, upsample=True):
     xyz32 = xyz.astype(np.float32)
@@ -105,7 +114,10 @@ def flex_conv_dilate(xyz, feat, p, prefix, dilate, outdims, knn=8, knn_indices=N
         knn_indices = knn_pm(pts, knn)
     for i, _ in enumerate(outdims):
         x = flexconv_bn_relu(x, pts, knn_indices, p, "%s.flexconv_%d" % (prefix, i))
-    if add_se:
+    if add_se == "avg_pool":   # core/backbones.py:79-82
+        x_pool = flex_avg_pm(x.astype(np.float32), pts, knn_indices, p, prefix + ".se_avgpool") * (1.0 / knn)
+        x = se_block(x, x_pool, p, prefix + ".se")
+    elif add_se:
         x = se_block(x, flex_pool_pm(x.astype(np.float32), knn_indices), p, prefix + ".se")
     if upsample and dilate > 1:
         dist, idx = oracle.three_nn(xyz32, pts)
@@ -117,7 +129,7 @@ def flex_conv_dilate(xyz, feat, p, prefix, dilate, outdims, knn=8, knn_indices=N
     return x
 
 
-def backbone_local_dilate(points, p, knn_ind, prefix="local"):
+def backbone_local_dilate(points, p, knn_ind, prefix="local", add_se="max_pool"):
     pts32 = points.astype(np.float32)
     nn8 = knn_ind[:, :, :8]
     f = oracle.convolution_pointset(np.transpose(pts32, (0, 2, 1)), np.transpose(nn8, (0, 2, 1)),
@@ -126,10 +138,14 @@ def backbone_local_dilate(points, p, knn_ind, prefix="local"):
     f = np.transpose(f, (0, 2, 1)).astype(np.float64)
     f = np.maximum(_bn(f, p, prefix + ".initconv_bn", TP_EPS), 0.0)
     f = flex_pool_pm(f.astype(np.float32), nn8)
-    x1 = flex_conv_dilate(points, f, p, prefix + ".stage1", 1, [64, 64], knn_indices=nn8, concat=False)
+    x1 = flex_conv_dilate(points, f, p, prefix + ".stage1", 1, [64, 64], knn_indices=nn8, concat=False,
+                          add_se=add_se)
     x2 = conv1x1(x1, p, prefix + ".before_stage2_conv1d.tfconv0")
-    x2 = flex_conv_dilate(points, x2, p, prefix + ".stage2", 8, [128, 128], concat=True)
-    return conv1x1(x1, p, prefix + ".local_stage1_shortcut.tfconv0") + x2
+    x2 = flex_conv_dilate(points, x2, p, prefix + ".stage2", 8, [128, 128], concat=True, add_se=add_se)
+    feat = conv1x1(x1, p, prefix + ".local_stage1_shortcut.tfconv0") + x2
+    if prefix + ".final_fc.tfconv0.W" in p:     # featdim < 128 (core/backbones.py:125-126)
+        feat = conv1x1(feat, p, prefix + ".final_fc.tfconv0")
+    return feat
 
 
 def attention_head(x, p, prefix, n):
@@ -165,19 +181,28 @@ def netvlad(features, att, p, prefix="netvlad", final_l2norm=True):
     return l2_normalize(vlad, -1, 1e-8) if final_l2norm else vlad
 
 
-def forward(points, p, detection=True, extract_global=True, knn_num=8, reference_cpu=False):
-    """The inference branch of DH3D.build_graph.  points [B,N,3]."""
+def forward(points, p, detection=True, extract_global=True, knn_num=8, reference_cpu=False, add_se="max_pool",
+            gl_dims=(256,), global_subsample=-1):
+    """The inference branch of DH3D.build_graph.  points [B,N,3].  If ``p`` carries a second backbone under
+    'global_local.' (the global checkpoint's own copy), the global branch runs on it -- the reference's two
+    separately trained networks evaluated on the same cloud."""
     _MODE["reference_cpu"] = bool(reference_cpu)
     points = np.asarray(points, np.float32)
     knn = knn_pm(points, knn_num)
     pts64 = points.astype(np.float64)
-    feat = backbone_local_dilate(pts64, p, knn)
+    feat = backbone_local_dilate(pts64, p, knn, add_se=add_se)
     out = {"feat": feat, "local_desc": l2_normalize(feat, 2, 1e-8), "knn": knn}
     if detection:
         out["attention"] = attention_head(feat, p, "detection_block_reliable", 3)
     if extract_global:
-        fg = flex_conv_dilate(pts64, feat, p, "global_before_assemble", 8, [256], concat=False,
+        gfeat = feat
+        if "global_local.initconv.position_theta" in p:
+            gfeat = backbone_local_dilate(pts64, p, knn, prefix="global_local", add_se=add_se)
+        fg = flex_conv_dilate(pts64, gfeat, p, "global_before_assemble", 8, list(gl_dims), concat=False,
                               add_se=False)
+        if global_subsample > 0:    # core/model.py:118-121
+            kp = oracle.farthest_point_sample(global_subsample, points)
+            fg = np.take_along_axis(fg, kp[:, :, None].astype(np.int64), axis=1)
         att = attention_head(fg, p, "globalatt", 1)
         out["forglobal"], out["global_att"] = fg, att
         out["globaldesc"] = netvlad(fg, att, p)

@@ -82,11 +82,12 @@ def main():
     if args.limit:
         names, clouds = names[:args.limit], clouds[:args.limit]
     print("%d clouds, %d padded with duplicated points" % (len(names), int((ori < 8192).sum())))
-    model = DH3D(full_config())
-    loaded, missing = load_reference_checkpoint(
+    # both reference networks in one pass: the detector on the local checkpoint's backbone, the global branch on
+    # the global checkpoint's own (differently trained) copy
+    model = DH3D(full_config(), separate_global_backbone=True)
+    load_reference_checkpoint(
         model, os.path.join(args.root, "models", "local", "localmodel"),
         os.path.join(args.root, "models", "global", "globalmodel"))
-    assert not missing, missing
     if args.backend == "gpu":
         import torch
         model = model.cuda()

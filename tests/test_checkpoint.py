@@ -19,8 +19,11 @@ def test_read_bundle_and_fill_every_model_parameter():
     assert np.isfinite(g["hidden1_weights"]).all() and abs(float(g["hidden1_weights"].std())) > 1e-4
     assert tf_name_to_param("stage1/flexconv_0_bn/mean/EMA") == "local.stage1.flexconv_0_bn.mean_ema"
     assert tf_name_to_param("cluster_bn/moving_variance") == "netvlad.cluster_bn.variance_ema"
-    assert tf_name_to_param("stage1/flexconv_0/position_theta/Adam_1") is None
-    model = DH3D(full_config())
+    # optimizer slots map to names no model has; the loader filters on the model, not on name heuristics
+    assert tf_name_to_param("stage1/flexconv_0/position_theta/Adam_1") == "local.stage1.flexconv_0.position_theta.Adam_1"
+    assert tf_name_to_param("stage1/flexconv_0/position_theta", "global_local") == \
+        "global_local.stage1.flexconv_0.position_theta"
+    model = DH3D(full_config(), separate_global_backbone=True)
     loaded, missing = load_reference_checkpoint(model, os.path.join(REF, "local", "localmodel"),
                                                 os.path.join(REF, "global", "globalmodel"))
     assert missing == [] and len(loaded) == len(list(model.named_parameters()))
@@ -30,6 +33,56 @@ def test_read_bundle_and_fill_every_model_parameter():
     l = read_tensor_bundle(os.path.join(REF, "local", "localmodel"))
     assert np.array_equal(p["detection_block_reliable.detec_conv_fc.W"].numpy(),
                           l["detection_block_reliable/detec_conv_fc/W"])
+
+
+def test_two_checkpoints_never_silently_share_one_backbone():
+    """the shipped local and global checkpoints carry DIFFERENT backbones; loading both into a
+    one-backbone model must not silently evaluate the detector on the global run's backbone."""
+    from dh3d_b200.checkpoint import (CheckpointError, checkpoint_model, load_reference_checkpoint,
+                                      read_tensor_bundle)
+    from dh3d_b200.configs import detection_config, full_config, global_config
+    from dh3d_b200.model import DH3D
+    lp, gp = os.path.join(REF, "local", "localmodel"), os.path.join(REF, "global", "globalmodel")
+    l, g = read_tensor_bundle(lp), read_tensor_bundle(gp)
+    k = "stage1/flexconv_0/position_theta"
+    assert np.abs(l[k] - g[k]).max() > 1e-2          # they really differ
+    with pytest.raises(CheckpointError, match="different backbones"):
+        load_reference_checkpoint(DH3D(full_config()), lp, gp)
+    for which, src in (("local", l), ("global", g)):
+        m = DH3D(full_config())
+        load_reference_checkpoint(m, lp, gp, shared_backbone=which)
+        p = dict(m.named_parameters())
+        assert np.array_equal(p["local.stage1.flexconv_0.position_theta"].numpy(), src[k])
+        assert np.array_equal(p["netvlad.gating_weights"].numpy(), g["gating_weights"])
+        assert np.array_equal(p["detection_block_reliable.detec_conv_fc.W"].numpy(),
+                              l["detection_block_reliable/detec_conv_fc/W"])
+    # separate backbones: each network keeps its own
+    m = checkpoint_model(lp, gp)
+    p = dict(m.named_parameters())
+    assert np.array_equal(p["local.stage1.flexconv_0.position_theta"].numpy(), l[k])
+    assert np.array_equal(p["global_local.stage1.flexconv_0.position_theta"].numpy(), g[k])
+    # strict: a branch the checkpoint does not carry raises instead of staying at its zero init
+    with pytest.raises(CheckpointError, match="neither checkpoint"):
+        load_reference_checkpoint(DH3D(full_config()), lp, None)
+    with pytest.raises(CheckpointError, match="neither checkpoint"):
+        load_reference_checkpoint(DH3D(detection_config()), None, gp)
+    loaded, missing = load_reference_checkpoint(DH3D(full_config()), lp, None, strict=False)
+    assert any(n.startswith("netvlad.") for n in missing)
+    assert load_reference_checkpoint(DH3D(global_config()), None, gp)[1] == []
+    assert load_reference_checkpoint(DH3D(detection_config()), lp, None)[1] == []
+
+
+def test_staged_weights_equal_the_checkpoints():
+    """oracle/_ref/dh3d_weights.npz (what the GPU-box tests read) == the shipped TensorBundles."""
+    from dh3d_b200.checkpoint import read_tensor_bundle
+    from oracle import build_ref
+    staged = build_ref.load_staged_weights()
+    if staged is None:
+        pytest.skip("weights not staged")
+    for tag, st in zip(("local", "global"), staged):
+        full = read_tensor_bundle(os.path.join(REF, tag, tag + "model"))
+        assert all(np.array_equal(v, full[k]) for k, v in st.items())
+        assert "hidden1_weights" in st or tag == "local"
 
 
 def test_data_helpers_on_demo_cloud():
@@ -62,8 +115,9 @@ def test_real_weights_demo_descriptors_match_gpu_golden():
     assert gold["recall"][:, 0].min() >= 0.7 and gold["recall"][:, 1].min() >= 0.9   # recall@1 / @5
     names, clouds, ori = prepare("/root/reference")
     assert list(names) == list(gold["names"]) and int((ori < 8192).sum()) == 15
-    model = DH3D(full_config())
-    load_reference_checkpoint(model, os.path.join(REF, "local", "localmodel"), os.path.join(REF, "global", "globalmodel"))
+    model = DH3D(full_config())   # the stored descriptors were made on the global checkpoint's backbone
+    load_reference_checkpoint(model, os.path.join(REF, "local", "localmodel"), os.path.join(REF, "global", "globalmodel"),
+                              shared_backbone="global")
     params = {k: v.detach().numpy() for k, v in model.named_parameters()}
     padded = int(np.nonzero(ori < 8192)[0][0])
     for i in (0, padded, 99):

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "dh3d_group_point_ld": (_c_int, [_c_int] * 5 + [_p, _c_int, _p, _p, _p]),
     "dh3d_three_interpolate_ld": (_c_int, [_c_int] * 4 + [_p, _p, _p, _c_int, _p, _c_int, _p]),
     "dh3d_add_l2_normalize_rows": (_c_int, [_p, _p, _p, _p, _c_int, _c_int, _c_float, _p]),
+    "dh3d_affine": (_c_int, [_p, _c_float, _c_float, _p, _c_size_t, _p]),
+    "dh3d_gather_rows": (_c_int, [_c_int] * 4 + [_p, _p, _p, _c_int, _p]),
     "dh3d_keypoint_nms_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "dh3d_keypoint_nms": (_c_int, [_p, _p, _c_int, _c_int, _c_float, _c_float, _c_int, _c_int, _p, _p, _p,
                                    _c_size_t, _p]),

@@ -164,8 +164,9 @@ class LocalBackbone(nn.Module):
         self.local_stage1_shortcut = FeatureConv1d(64, 128)
         self.final_fc = FeatureConv1d(128, featdim) if featdim < 128 else None
 
-    def forward(self, points, knn_ind, geometry=None, with_desc=False):
-        """-> feat [B,N,128]; with_desc=True: (feat, l2-normalised feat) from one fused pass (model.py:177-181)."""
+    def forward(self, points, knn_ind, geometry=None, with_desc=False, desc_out=None):
+        """-> feat [B,N,128]; with_desc=True: (feat, l2-normalised feat) from one fused pass (model.py:177-181).
+        ``desc_out``: caller-owned [B,N,featdim] tensor the normalised descriptors are written into."""
         nn_8 = knn_ind if knn_ind.shape[2] == 8 else knn_ind[:, :, :8].contiguous()
         f = self.initconv.forward_pm(points, nn_8, bn=self.initconv_bn, act=ACT_RELU)
         f = ops.flex_pool(f, nn_8)
@@ -184,15 +185,19 @@ class LocalBackbone(nn.Module):
         want_desc = with_desc and self.final_fc is None
         if fused:
             cat = self.stage2(points, None, geometry=geometry, cat=cat, defer_concat=True)
-            y = ops.linear_join(cat, pa, sa, ba, la.act, x1, pb, sb, bb, lb.act, eps=1e-8 if want_desc else None)
+            y = ops.linear_join(cat, pa, sa, ba, la.act, x1, pb, sb, bb, lb.act, eps=1e-8 if want_desc else None,
+                                out_norm=desc_out if want_desc else None)
         else:
             x2 = self.stage2(points, None, geometry=geometry, cat=cat)
             sc = self.local_stage1_shortcut(x1)
             y = ops.add_l2_normalize_rows(sc, x2, 1e-8) if want_desc else ops.add(sc, x2)
+            if want_desc and desc_out is not None:
+                ops.copy_cols(y[1], desc_out, 0)
+                y = (y[0], desc_out)
         if self.final_fc is None:
             return y
         y = self.final_fc(y)   # featdim < 128 (core/backbones.py:125-126): Conv2D + BN + ReLU, then the l2 norm
-        return (y, ops.l2_normalize_rows(y, 1e-8)) if with_desc else y
+        return (y, ops.l2_normalize_rows(y, 1e-8, out=desc_out)) if with_desc else y
 
 
 class AttentionHead(FoldedModule):
@@ -209,7 +214,8 @@ class AttentionHead(FoldedModule):
         self.detec_conv_fc = Conv1x1(c, 1, bn=False, act=ACT_NONE)
         self._folded = None
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """``out``: caller-owned [B,N,1] tensor for the attention."""
         if self._folded is None:
             fc = self.detec_conv_fc
             self._folded = (fc.W.reshape(-1).contiguous(), float(fc.b.reshape(-1)[0].item()))
@@ -219,8 +225,14 @@ class AttentionHead(FoldedModule):
         last = getattr(self, "detec_conv%d" % (self.n - 1))
         w, scale, shift, packed = last.folded()
         if packed is not None:  # fused: the [B,N,1024] hidden layer never reaches HBM
-            return ops.linear_rowdot(x, packed, scale, shift, last.act, w2, b2, ACT_SIGMOID).unsqueeze(-1)
-        return ops.rowdot(last(x), w2, bias=b2, act=ACT_SIGMOID).unsqueeze(-1)  # [B,N,1]
+            y = ops.linear_rowdot(x, packed, scale, shift, last.act, w2, b2, ACT_SIGMOID,
+                                  out=None if out is None else out.view(out.shape[:-1]))
+            return y.unsqueeze(-1)
+        y = ops.rowdot(last(x), w2, bias=b2, act=ACT_SIGMOID).unsqueeze(-1)  # [B,N,1]
+        if out is not None:
+            ops.copy_cols(y, out, 0)
+            return out
+        return y
 
 
 class DetectionBlock(AttentionHead):
@@ -249,13 +261,13 @@ class GlobalNetVLADBlock(FoldedModule):
         self.gating_bn = BatchNorm(output_dim, eps=SLIM_BN_EPS)
         self._folded = None
 
-    def forward(self, xyz, features, att, final_l2norm=True):
+    def forward(self, xyz, features, att, final_l2norm=True, out=None):
         if self._folded is None:
             self._folded = (self.cluster_bn.fold(), self.bn.fold(), self.gating_bn.fold(),
                             self.cluster_weights2.reshape(self.cluster_weights.shape).contiguous())
         cbn, bn, gbn, cw2 = self._folded
         return ops.netvlad(features, att, self.cluster_weights, cbn, cw2, self.hidden1_weights, bn,
-                           self.gating_weights, gbn, final_l2norm=final_l2norm)
+                           self.gating_weights, gbn, final_l2norm=final_l2norm, out=out)
 
 
 def global_netvald_block(xyz, features, att, is_training=False, cluster_size=64, output_dim=256, add_batch_norm=True,

@@ -118,6 +118,9 @@ int group_point_grad_launch(int b, int n, int c, int m, int nsample, const float
 int three_interpolate_grad_launch(int b, int n, int c, int m, const float* grad_out, const int32_t* idx,
                                   const float* weight, float* grad_points, cudaStream_t st);
 // nms.cu
+int affine_launch(const float* x, float a, float b, float* y, size_t n, cudaStream_t st);
+int gather_rows_launch(int b, int n, int c, int m, const float* src, const int32_t* idx, float* out, int ldo,
+                       cudaStream_t st);
 size_t keypoint_nms_workspace_bytes(int B, int N);
 int keypoint_nms_launch(const float* xyz, const float* attention, int B, int N, float nms_radius,
                         float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
@@ -431,6 +434,13 @@ int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float* grad_ou
   return three_interpolate_grad_launch(b, n, c, m, grad_out, idx, weight, grad_points, S(stream));
 }
 
+int dh3d_affine(const float* x, float a, float b, float* y, size_t count, void* stream) {
+  return affine_launch(x, a, b, y, count, S(stream));
+}
+int dh3d_gather_rows(int b, int n, int c, int m, const float* src, const int32_t* idx, float* out, int ldo,
+                     void* stream) {
+  return gather_rows_launch(b, n, c, m, src, idx, out, ldo, S(stream));
+}
 size_t dh3d_keypoint_nms_workspace_bytes(int B, int N) { return keypoint_nms_workspace_bytes(B, N); }
 int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int B, int N, float nms_radius,
                       float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,

@@ -6,10 +6,17 @@
 //     x' = x * 2^4          = xh + xl      (xh = fp16(x'), xl = fp16(x' - xh))
 //     w' = w * sw[n]        = wh + wl      (sw[n] = power of two putting max_k |w[k,n]| in [2^13, 2^14))
 //     x'*w' ~= xl*wh + xh*wl + xh*wh       (dropped xl*wl ~ 2^-22 relative), result * 2^-4 / sw[n]
-// fp16 has 5 exponent bits, hence the scaling: the low parts stay normal (or lose at most 2^-25
-// absolute = 2^-29 of |x| = 1) for activations with |x| in [2^-12, 4094]; an activation beyond that
-// converts to inf and the output row turns inf/NaN (loud, never silently wrong).  Weight columns are
-// scaled individually, so any weight magnitude works.  DH3D_GEMM_SPLIT=tf32 selects gemm_tc.cu instead.
+// fp16 has 5 exponent bits, hence the scaling.  Weight columns are scaled individually, so any weight
+// magnitude works.  Activations are scaled by the FIXED 2^4 (a per-row scale would need the row maximum
+// before the first K slab is split): the split is fp32-grade for rows whose largest |x| lies in
+// [2^-11, 3750] -- above, x*2^4 overflows fp16; below, the low parts go subnormal (2^-25 absolute) and the
+// row loses relative precision.  Rows OUTSIDE that window (and rows holding inf / NaN) are not left to the
+// tensor cores: the split warps track every row's largest |x| while they convert it (integer max on the
+// values already in registers), out-of-window rows are queued in shared memory, and after its tile loop the
+// CTA recomputes just those rows with plain fp32 FFMA from the same (wh + wl) weights and overwrites them.
+// In-distribution activations (post-BatchNorm / ReLU, O(1)) never queue a row, so the hot path pays one
+// IMNMX per element on the first N pass and a never-taken branch; out-of-distribution clouds cost
+// ~3 us per affected row instead of poisoning the descriptors (round-1 ADVICE / VERDICT item 5).
 //
 // Same persistent warp-specialised structure as gemm_tc.cu (320 threads, one CTA per SM, 2-CTA
 // clusters multicasting the W tiles), with
@@ -29,6 +36,38 @@ namespace dh3d {
 constexpr int kT16Threads = 320;
 constexpr float kT16XScale = 16.f;         // 2^4
 constexpr float kT16XScaleInv = 0.0625f;
+// safe window of a row's largest |x| for the fixed-scale fp16 split, as (float bits << 1) (monotone in |x|;
+// inf / NaN compare above every finite value)
+constexpr uint32_t kT16HiBits2 = 0x456A6000u << 1;   // 3750.0f
+constexpr uint32_t kT16LoBits2 = 0x3A000000u << 1;   // 2^-11
+constexpr int kT16BadCap = 1024;                     // queued out-of-window rows per CTA (more: redo all its rows)
+constexpr uint32_t kT16BadBytes = 16 + kT16BadCap * 4;
+
+__device__ __forceinline__ uint32_t t16_absmax8(uint32_t m, const float4& a, const float4& b) {
+  m = max(m, __float_as_uint(a.x) << 1); m = max(m, __float_as_uint(a.y) << 1);
+  m = max(m, __float_as_uint(a.z) << 1); m = max(m, __float_as_uint(a.w) << 1);
+  m = max(m, __float_as_uint(b.x) << 1); m = max(m, __float_as_uint(b.y) << 1);
+  m = max(m, __float_as_uint(b.z) << 1); m = max(m, __float_as_uint(b.w) << 1);
+  return m;
+}
+__device__ __forceinline__ bool t16_row_out_of_window(uint32_t m2) {
+  return m2 > kT16HiBits2 || (m2 != 0u && m2 < kT16LoBits2);
+}
+// split-warp thread (chunk c = t & 3 of rows (t >> 2) + 32 i): reduce the 4 chunk owners of each row and queue
+// the rows whose maximum left the window.  bad[0] = count, bad[4..] = global row indices.
+__device__ __forceinline__ void t16_queue_bad_rows(uint32_t (&rmax)[4], int t, int row0, uint32_t* bad) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t m = rmax[i];
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    rmax[i] = 0u;
+    if ((t & 3) == 0 && t16_row_out_of_window(m)) {
+      const uint32_t slot = atomicAdd(&bad[0], 1u);
+      if (slot < (uint32_t)kT16BadCap) bad[4 + slot] = (uint32_t)(row0 + (t >> 2) + 32 * i);
+    }
+  }
+}
 
 template <int BN>
 struct T16Cfg {
@@ -39,7 +78,7 @@ struct T16Cfg {
   static constexpr uint32_t kStageBytes = kRawBytes + 2 * kABytes + 2 * kBBytes;
   static constexpr uint32_t kParamBytes = 2 * 3 * BN * 4;    // double-buffered scale/shift/w2 slices
   static constexpr uint32_t kSmemBytes =
-      kStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+      kStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + kT16BadBytes + 1024 /*align*/;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
@@ -52,7 +91,61 @@ struct T16Epilogue {
   float b2;
   int act2;
   float* y2;              // [M]   (ROWDOT mode)
+  // what the fp32 recompute of out-of-window rows reads / writes (raw pointers next to the tensor maps)
+  const float* x; int ldx;
+  const __half* wh; const __half* wl; int Kp;
+  float* y; int ldy;
 };
+
+// x[row, 0:K] . (wh + wl)[n, 0:K] by one warp: lane l owns k = 8l .. 8l+7 (+256 per round), 16-byte loads of the
+// K-major weight rows (Kp is a multiple of 8 and zero padded) and of the activation row; every lane gets the sum.
+__device__ __forceinline__ float t16_row_dot(const float* __restrict__ xr, const __half* __restrict__ h,
+                                             const __half* __restrict__ l, int K, int lane) {
+  float acc = 0.f;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h + k0));
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(l + k0));
+    const float4 x0 = ldg4(xr + k0);
+    const float4 x1 = (k0 + 4 < K) ? ldg4(xr + k0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);   // K % 4 == 0 only
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+      acc = fmaf(xs[2 * i], a.x + b.x, acc);          // wh + wl is exact in fp32 (22 significant bits)
+      acc = fmaf(xs[2 * i + 1], a.y + b.y, acc);
+    }
+  }
+  return warp_sum(acc);
+}
+
+// fp32 recompute of one output row by the whole CTA, one warp per output column (out-of-window rows only; see
+// the header).  y[row, n] = act((x[row, :] @ W[:, n]) * scale[n] + shift[n]) with W = (wh + wl) * colscale * 2^4.
+template <bool ROWDOT>
+__device__ __noinline__ void t16_fixup_row(const T16Epilogue& ep, int row, int K, int N, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* xr = ep.x + (long long)row * ep.ldx;
+  float part = 0.f;
+  for (int n = warp; n < N; n += nw) {
+    const float acc = t16_row_dot(xr, ep.wh + (long long)n * ep.Kp, ep.wl + (long long)n * ep.Kp, K, lane);
+    float v = acc * (__ldg(ep.colscale + n) * kT16XScale);
+    v = fmaf(v, ep.scale ? __ldg(ep.scale + n) : 1.f, ep.shift ? __ldg(ep.shift + n) : 0.f);
+    v = tc_act(v, ep.act);
+    if constexpr (ROWDOT) part = fmaf(v, __ldg(ep.w2 + n), part);
+    else if (lane == 0) ep.y[(long long)row * ep.ldy + n] = v;
+  }
+  if constexpr (ROWDOT) {
+    __syncthreads();
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < nw; ++w) tot += red[w];
+      ep.y2[row] = tc_act(tot + ep.b2, ep.act2);
+    }
+  }
+}
 
 // K-major, 64B-swizzled operand tile: rows 64 B apart, 8-row groups 512 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
@@ -113,6 +206,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bars + 3 * S;       // [2] accumulator ready    (count 1, tcgen05.commit)
   uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] accumulator drained  (count 4, one per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  uint32_t* bad = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [0] count, [4..] rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + kTcBK - 1) / kTcBK;
@@ -131,6 +225,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   };
 
   if (threadIdx.x == 0) {
+    bad[0] = 0u;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&conv[s], 128);
@@ -225,8 +320,9 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int t = threadIdx.x - 64;  // 0..127
     const int c = t & 3;
     uint32_t it = 0;
+    uint32_t rmax[4] = {0u, 0u, 0u, 0u};   // largest |x| (bits << 1) of this thread's 4 rows over the tile's K slabs
     for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
-      for (int nt = 0; nt < num_nt; ++nt)
+      for (int nt = 0; nt < num_nt; ++nt) {
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
@@ -239,6 +335,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int r = (t >> 2) + 32 * i;
             const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
             const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
+            if (nt == 0) rmax[i] = t16_absmax8(rmax[i], v0, v1);   // the later N passes re-read the same rows
             uint4 hi, lo;
             split8(v0, v1, hi, lo);
             const uint32_t off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
@@ -248,6 +345,8 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async();
           mbar_arrive(&conv[s]);
         }
+        if (nt == 0) t16_queue_bad_rows(rmax, t, (mtb + (int)crank) * kTcBM, bad);
+      }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 6..9)
     const int q = warp & 3;              // TMEM lane quadrant of this warp
@@ -325,6 +424,20 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(Cfg::kTmemCols)
                  : "memory");
+  }
+  // out-of-window rows (never in-distribution): fp32 recompute over the tensor-core result; every TMA store of
+  // this CTA has completed (epilogue warps waited on their bulk groups before the barrier above)
+  const uint32_t nbad = bad[0];
+  if (nbad != 0u) {
+    if (nbad <= (uint32_t)kT16BadCap) {
+      for (uint32_t i = 0; i < nbad; ++i) t16_fixup_row<ROWDOT>(ep, (int)bad[4 + i], K, N, params);
+    } else {   // queue overflowed: redo every row this CTA owns
+      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
+        for (int r = 0; r < kTcBM; ++r) {
+          const int row = (mtb + (int)crank) * kTcBM + r;
+          if (row < M) t16_fixup_row<ROWDOT>(ep, row, K, N, params);
+        }
+    }
   }
 }
 
@@ -478,7 +591,7 @@ int linear_tc16_launch(const float* x, int ldx, const void* packed, const float*
   if (ldy % 4 || ldy < N) return DH3D_ERR_DIM;
   if ((((uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) != 0) return DH3D_ERR_ALIGN;
   const T16Packed p = t16_unpack(packed, K, N);
-  T16Epilogue ep{scale, shift, p.cs, act, nullptr, 0.f, 0, nullptr};
+  T16Epilogue ep{scale, shift, p.cs, act, nullptr, 0.f, 0, nullptr, x, ldx, p.wh, p.wl, t16_kp(K), y, ldy};
   if (N <= 32) return launch_t16<32, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
   if (N <= 64) return launch_t16<64, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
   if (N <= 128) return launch_t16<128, false>(x, ldx, p.wh, p.wl, ep, y, ldy, M, K, N, st);
@@ -492,7 +605,7 @@ int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const
   if (rc != DH3D_OK) return rc;
   if (!w2 || !y2) return DH3D_ERR_NULL;
   const T16Packed p = t16_unpack(packed, K, N);
-  T16Epilogue ep{scale, shift, p.cs, act, w2, b2, act2, y2};
+  T16Epilogue ep{scale, shift, p.cs, act, w2, b2, act2, y2, x, ldx, p.wh, p.wl, t16_kp(K), nullptr, 0};
   if (N <= 64) return launch_t16<64, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
   if (N <= 128) return launch_t16<128, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
   return launch_t16<256, true>(x, ldx, p.wh, p.wl, ep, nullptr, 0, M, K, N, st);
@@ -519,7 +632,7 @@ struct JoinCfg {
   static constexpr uint32_t kStageBytes = kRawBytes + 2 * kABytes + 2 * kBBytes;
   static constexpr uint32_t kParamBytes = 2 * 4 * kJBN * 4;   // [tile parity][sA*csA, bA, sB*csB, bB][128]
   static constexpr uint32_t kSmemBytes =
-      kJStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+      kJStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + kT16BadBytes + 1024 /*align*/;
 };
 
 struct JoinArgs {
@@ -528,7 +641,41 @@ struct JoinArgs {
   float eps;
   int has_norm;
   int M, Ka, Kb;
+  // for the fp32 recompute of out-of-window rows
+  const float* xa; int ldxa; const __half* wah; const __half* wal; int Kpa;
+  const float* xb; int ldxb; const __half* wbh; const __half* wbl; int Kpb;
+  float* y; int ldy; float* yn; int ldn;
 };
+
+// fp32 recompute of one row of the join, one warp per output column; red = 128 values + one slot per warp
+__device__ __noinline__ void join16_fixup_row(const JoinArgs& a, int row, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* xa = a.xa + (long long)row * a.ldxa;
+  const float* xb = a.xb + (long long)row * a.ldxb;
+  float ss = 0.f;
+  __syncthreads();   // red is reused row after row
+  for (int n = warp; n < kJBN; n += nw) {
+    float va = t16_row_dot(xa, a.wah + (long long)n * a.Kpa, a.wal + (long long)n * a.Kpa, a.Ka, lane);
+    va *= __ldg(a.cs_a + n) * kT16XScale;
+    va = tc_act(fmaf(va, a.scale_a ? __ldg(a.scale_a + n) : 1.f, a.shift_a ? __ldg(a.shift_a + n) : 0.f), a.act_a);
+    float vb = t16_row_dot(xb, a.wbh + (long long)n * a.Kpb, a.wbl + (long long)n * a.Kpb, a.Kb, lane);
+    vb *= __ldg(a.cs_b + n) * kT16XScale;
+    vb = tc_act(fmaf(vb, a.scale_b ? __ldg(a.scale_b + n) : 1.f, a.shift_b ? __ldg(a.shift_b + n) : 0.f), a.act_b);
+    const float v = va + vb;
+    ss = fmaf(v, v, ss);
+    if (lane == 0) {
+      a.y[(long long)row * a.ldy + n] = v;
+      red[n] = v;
+    }
+  }
+  if (a.has_norm) {
+    if (lane == 0) red[kJBN + warp] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nw; ++w) tot += red[kJBN + w];
+    if (threadIdx.x < kJBN) a.yn[(long long)row * a.ldn + threadIdx.x] = red[threadIdx.x] * rsqrtf(fmaxf(tot, a.eps));
+  }
+}
 
 __global__ void __launch_bounds__(kT16Threads, 1)
 gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmWah,
@@ -550,6 +697,7 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
   uint64_t* tmem_full = bars + 3 * S;       // [2] both accumulators of a tile ready
   uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] drained (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  uint32_t* bad = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb_a = (a.Ka + kTcBK - 1) / kTcBK, nkb_b = (a.Kb + kTcBK - 1) / kTcBK;
@@ -565,6 +713,7 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
   };
 
   if (threadIdx.x == 0) {
+    bad[0] = 0u;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&conv[s], 128);
@@ -643,7 +792,8 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
     const int t = threadIdx.x - 64;
     const int c = t & 3;
     uint32_t it = 0;
-    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+    uint32_t rmax[4] = {0u, 0u, 0u, 0u};   // over BOTH branches' slabs: either input leaving the window queues the row
+    for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -656,6 +806,7 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
           const int r = (t >> 2) + 32 * i;
           const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
           const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
+          rmax[i] = t16_absmax8(rmax[i], v0, v1);
           uint4 hi, lo;
           split8(v0, v1, hi, lo);
           const uint32_t off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
@@ -665,6 +816,8 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
         fence_proxy_async();
         mbar_arrive(&conv[s]);
       }
+      t16_queue_bad_rows(rmax, t, mt * kTcBM, bad);
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 6..9)
     const int q = warp & 3;
@@ -741,6 +894,16 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+  const uint32_t nbad = bad[0];   // out-of-window rows: fp32 recompute (see the header of this file)
+  if (nbad != 0u) {
+    if (nbad <= (uint32_t)kT16BadCap) {
+      for (uint32_t i = 0; i < nbad; ++i) join16_fixup_row(a, (int)bad[4 + i], params);
+    } else {
+      for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
+        for (int r = 0; r < kTcBM; ++r)
+          if (mt * kTcBM + r < a.M) join16_fixup_row(a, mt * kTcBM + r, params);
+    }
+  }
 }
 
 // packed_a / packed_b: linear_prepack16 buffers of Wa [Ka,128] / Wb [Kb,128]; yn may be null (no normalised copy)
@@ -768,7 +931,8 @@ int linear_join_tc16_launch(const float* xa, int ldxa, const void* packed_a, con
   if ((rc = make_map(&my, y, M, N, ldy, 32)) != DH3D_OK) return rc;
   if (yn) { if ((rc = make_map(&myn, yn, M, N, ldn, 32)) != DH3D_OK) return rc; }
   else myn = my;
-  JoinArgs a{scale_a, shift_a, pa.cs, act_a, scale_b, shift_b, pb.cs, act_b, eps, yn ? 1 : 0, M, Ka, Kb};
+  JoinArgs a{scale_a, shift_a, pa.cs, act_a, scale_b, shift_b, pb.cs, act_b, eps, yn ? 1 : 0, M, Ka, Kb,
+             xa, ldxa, pa.wh, pa.wl, t16_kp(Ka), xb, ldxb, pb.wh, pb.wl, t16_kp(Kb), y, ldy, yn, ldn};
   cudaError_t e = cudaFuncSetAttribute(gemm_join16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)JoinCfg::kSmemBytes);
   if (e != cudaSuccess) return (int)e;

@@ -104,12 +104,15 @@ __device__ __forceinline__ unsigned spread3(unsigned v) {  // 4 bits -> every th
 // sort: positions (any layout via strides) -> Morton-cell-sorted float4 (x,y,z,idx) + chunk boxes
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSortThreads, 1)
-knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int sp, int sd,
+knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int sp, int sd, int T, int logT, int logV,
                 float4* __restrict__ sorted, float4* __restrict__ boxes) {
   __shared__ int s_hist[kCells];
   __shared__ float s_red[6][kSortThreads / 32];
   __shared__ float s_box[6];
   __shared__ int s_wsum[kSortThreads / 32];
+  __shared__ int s_axis[3][64];   // per-axis occupancy histogram of the grid range (gap trimming)
+  __shared__ int s_changed[6];    // one flag per trimming round (no reuse: no reset race)
+  __shared__ int s_nout;          // points outside the trimmed grid range: their own bucket after the last cell
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = pos + (long long)b * sb;
   float4* out = sorted + (long long)b * Np;
@@ -150,21 +153,98 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
     }
   }
   __syncthreads();
-  float lo[3], inv[3];
+  // Gap trimming of the grid range.  The 16^3 grid spans [s_box lo, hi]; a few far points (the reference pads
+  // short clouds with points at 1e5 when randsample=False, core/utils.py:107-108; stray returns) would stretch it
+  // until every real point shares one cell and no box prunes anything (measured: k-NN 0.27 -> 1.24 ms).  Up to 6
+  // rounds: histogram each axis over 64 bins of its current range; if some run of EMPTY bins covers at least half
+  // of the occupied range, keep only the side of the gap that holds more points, then tighten to the occupied
+  // bins.  Well-spread clouds never have such a gap and keep their exact bounding box (round 0 changes nothing).  Points left outside the range are sorted into one extra bucket after the
+  // last cell (their own chunks, with whatever boxes they get), so they cannot inflate the boxes of real chunks.
+  // This only changes the SCAN ORDER and the pruning power, never the result.
+  for (int round = 0; round < 6; ++round) {
+    if (tid < 3 * 64) (&s_axis[0][0])[tid] = 0;
+    if (tid == 0) s_changed[round] = 0;
+    __syncthreads();
+    {
+      float rlo[3], rinv[3], rhi[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        rlo[d] = s_box[d];
+        rhi[d] = s_box[3 + d];
+        const float ext = rhi[d] - rlo[d];
+        rinv[d] = (ext > 0.f && ext < CUDART_INF_F) ? 64.f / ext : 0.f;
+      }
+      for (int i = tid; i < N; i += kSortThreads) {
+        float v[3];
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          v[d] = P[(long long)i * sp + d * sd];
+          in = in && (v[d] >= rlo[d]) && (v[d] <= rhi[d]);
+        }
+        if (in) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) atomicAdd(&s_axis[d][min(63, (int)((v[d] - rlo[d]) * rinv[d]))], 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 3) {
+      const int d = tid;
+      int first = -1, last = -1;
+      for (int bin = 0; bin < 64; ++bin)
+        if (s_axis[d][bin] != 0) { if (first < 0) first = bin; last = bin; }
+      if (first >= 0) {
+        int best_a = 0, best_len = 0, run_a = 0, run_len = 0;   // longest run of empty bins strictly inside
+        for (int bin = first; bin <= last; ++bin) {
+          if (s_axis[d][bin] == 0) {
+            if (run_len == 0) run_a = bin;
+            ++run_len;
+            if (run_len > best_len) { best_len = run_len; best_a = run_a; }
+          } else {
+            run_len = 0;
+          }
+        }
+        const int span = last - first + 1;
+        const float l0 = s_box[d], w = (s_box[3 + d] - s_box[d]) * (1.f / 64.f);
+        if (2 * best_len >= span && best_len >= 8) {        // a gap over half of the occupied range: keep the heavier side
+          int left = 0, right = 0;
+          for (int bin = first; bin < best_a; ++bin) left += s_axis[d][bin];
+          for (int bin = best_a + best_len; bin <= last; ++bin) right += s_axis[d][bin];
+          if (left >= right) { s_box[d] = l0 + w * (float)first; s_box[3 + d] = l0 + w * (float)best_a; }
+          else { s_box[d] = l0 + w * (float)(best_a + best_len); s_box[3 + d] = l0 + w * (float)(last + 1); }
+          s_changed[round] = 1;
+        } else if (span <= 48 && round > 0) {              // after a cut: tighten to the occupied bins
+          s_box[d] = l0 + w * (float)first;
+          s_box[3 + d] = l0 + w * (float)(last + 1);
+          s_changed[round] = 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (!s_changed[round]) break;
+  }
+  if (tid == 0) s_nout = 0;
+  float lo[3], hi[3], inv[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     lo[d] = s_box[d];
+    hi[d] = s_box[3 + d];
     const float ext = s_box[3 + d] - s_box[d];
     inv[d] = (ext > 0.f && ext < CUDART_INF_F) ? 16.f / ext : 0.f;
   }
   auto cell_of = [&](int i) -> int {
     unsigned c[3];
+    bool outside = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      const float v = (P[(long long)i * sp + d * sd] - lo[d]) * inv[d];
+      const float p = P[(long long)i * sp + d * sd];
+      outside = outside || (p < lo[d]) || (p > hi[d]);
+      const float v = (p - lo[d]) * inv[d];
       int q = (v >= 0.f) ? ((v < 15.f) ? (int)v : 15) : 0;  // NaN -> 0; only the scan order depends on it
       c[d] = (unsigned)q;
     }
+    if (outside) return kCells;
     // Hilbert index of the cell (Skilling's axes-to-transpose, 4 bits per axis): consecutive cells are always
     // face neighbours, so a window of consecutive sorted points has a compact bounding box (a Morton window
     // that straddles a block boundary spans far more space: ~80 chunks per warp had to be scanned, ncu r1l)
@@ -189,8 +269,14 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
   };
 
   // (2) histogram, (3) exclusive scan, (4) scatter
-  for (int i = tid; i < N; i += kSortThreads) atomicAdd(&s_hist[cell_of(i)], 1);
+  for (int i = tid; i < N; i += kSortThreads) {
+    const int c = cell_of(i);
+    atomicAdd(c < kCells ? &s_hist[c] : &s_nout, 1);
+  }
   __syncthreads();
+  const int n_inside = N - s_nout;
+  __syncthreads();
+  if (tid == 0) s_nout = 0;   // now the running position inside the outside bucket
   {
     constexpr int PER = kCells / kSortThreads;
     int v[PER], sum = 0;
@@ -221,7 +307,8 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
   }
   __syncthreads();
   for (int i = tid; i < N; i += kSortThreads) {
-    const int p = atomicAdd(&s_hist[cell_of(i)], 1);
+    const int c = cell_of(i);
+    const int p = c < kCells ? atomicAdd(&s_hist[c], 1) : n_inside + atomicAdd(&s_nout, 1);
     out[p] = make_float4(P[(long long)i * sp], P[(long long)i * sp + sd], P[(long long)i * sp + 2 * sd],
                          __int_as_float(i));
   }
@@ -235,11 +322,14 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
     float bmn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
     float bmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     const float4 q = out[c * kKnnChunk + lane];
+    int mr = INT_MAX;   // smallest tie rank in the chunk: with the box bound, a lower bound of every packed (key, rank)
     if (__float_as_int(q.w) >= 0) {
       bmn[0] = q.x; bmx[0] = q.x;
       bmn[1] = q.y; bmx[1] = q.y;
       bmn[2] = q.z; bmx[2] = q.z;
+      mr = knn_rank_of(__float_as_int(q.w), T, logT, logV);
     }
+    mr = __reduce_min_sync(0xffffffffu, mr);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -248,7 +338,7 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
         bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o));
       }
     if (lane == 0) {
-      bx[2 * c] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
+      bx[2 * c] = make_float4(bmn[0], bmn[1], bmn[2], __int_as_float(mr));
       bx[2 * c + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
     }
   }
@@ -257,10 +347,13 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
   float4* sbx = bx + 2 * nchunks;
   for (int s = warp; s < nsuper; s += kSortThreads / 32) {
     const int c = s * kKnnSuper + (lane & (kKnnSuper - 1));
-    float4 lo4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.f);
+    float4 lo4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(INT_MAX));
     float4 hi4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
     if (c < nchunks) { lo4 = bx[2 * c]; hi4 = bx[2 * c + 1]; }
     float bmn[3] = {lo4.x, lo4.y, lo4.z}, bmx[3] = {hi4.x, hi4.y, hi4.z};
+    int mr = __float_as_int(lo4.w);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mr = min(mr, __shfl_xor_sync(0xffffffffu, mr, o));
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -269,7 +362,7 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
         bmx[d] = fmaxf(bmx[d], __shfl_xor_sync(0xffffffffu, bmx[d], o));
       }
     if (lane == 0) {
-      sbx[2 * s] = make_float4(bmn[0], bmn[1], bmn[2], 0.f);
+      sbx[2 * s] = make_float4(bmn[0], bmn[1], bmn[2], __int_as_float(mr));
       sbx[2 * s + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
     }
   }
@@ -355,6 +448,7 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
 #pragma unroll
   for (int j = 0; j < KC; ++j) L[j] = kInit;
   float thr2 = active ? CUDART_INF_F : -1.f;  // inactive lanes never pass
+  unsigned long long kth_pk = kInit;           // the lane's current K-th packed (key, rank)
   int cnt = 0;
 
   auto flush = [&]() {
@@ -393,7 +487,19 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
 #pragma unroll
       for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
     }
+    kth_pk = kth;
     if (active) thr2 = M::bound(__uint_as_float((uint32_t)(kth >> 32)));
+  };
+
+  // Can a box still hold a candidate that enters this lane's list?  lb = lower bound of every d2 in the box
+  // (same op sequence as the distance, monotone roundings), minrank = smallest tie rank in the box: every
+  // candidate's packed (key, rank) is >= (key(lb), minrank) because key() is monotone.  The rank half is what
+  // keeps clouds with masses of EQUAL keys (duplicated padding points; the all-zero padding clouds of the
+  // reference's extractors, where every box bound ties with every list) from degenerating into a full scan.
+  auto box_can_enter = [&](float lb, int minrank) -> bool {
+    if (!(lb <= thr2)) return false;
+    const unsigned long long pk = ((unsigned long long)__float_as_uint(M::key(lb)) << 32) | (uint32_t)minrank;
+    return pk < kth_pk;
   };
 
   auto box_lb = [&](const float4* boxp, int c) -> float {
@@ -442,7 +548,7 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   for (int sstep = 0; sstep <= 2 * sreach; ++sstep) {
     const int sc = (sstep & 1) ? s0 + ((sstep + 1) >> 1) : s0 - (sstep >> 1);
     if (sc < 0 || sc >= nsuper) continue;
-    if (!__any_sync(0xffffffffu, box_lb(sbx, sc) <= thr2)) continue;
+    if (!__any_sync(0xffffffffu, box_can_enter(box_lb(sbx, sc), __float_as_int(__ldg(sbx + 2 * sc).w)))) continue;
     const int cbeg = sc * kKnnSuper, cend = min(cbeg + kKnnSuper, nchunks);
     const int cn = cend - cbeg;
     float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
@@ -473,10 +579,11 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
                     lz = __shfl_sync(0xffffffffu, blo.z, j);
         const float hx = __shfl_sync(0xffffffffu, bhi.x, j), hy = __shfl_sync(0xffffffffu, bhi.y, j),
                     hz = __shfl_sync(0xffffffffu, bhi.z, j);
+        const int mr = __shfl_sync(0xffffffffu, __float_as_int(blo.w), j);
         const float ex = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
         const float ey = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
         const float ez = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
-        if (!__any_sync(0xffffffffu, M::d2(ex, ey, ez) <= thr2)) continue;
+        if (!__any_sync(0xffffffffu, box_can_enter(M::d2(ex, ey, ez), mr))) continue;
       }
       // one coalesced 512-byte load per chunk, staged in the warp's shared-memory slot and read back as LDS.128
       // broadcasts
@@ -569,7 +676,7 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   const int Np = knn_padded(N);
   float4* sorted = reinterpret_cast<float4*>(workspace);
   float4* boxes = sorted + (size_t)B * Np;
-  knn_sort_kernel<<<B, kSortThreads, 0, st>>>(pos, N, Np, sb, sp, sd, sorted, boxes);
+  knn_sort_kernel<<<B, kSortThreads, 0, st>>>(pos, N, Np, sb, sp, sd, o.T, o.logT, o.logV, sorted, boxes);
   int rc = launch_status();
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(Np, kKnnThreads), B);
@@ -615,10 +722,11 @@ int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* 
   float4* boxes = cands + (size_t)b * np2;
   float4* queries = boxes + (size_t)b * knn_box_f4(np2);
   float4* qboxes = queries + (size_t)b * np1;
-  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, queries, qboxes);
+  // tie rank of the 3-NN metric = the index itself (T = 2^30, V = 1)
+  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, 1 << 30, 30, 0, queries, qboxes);
   int rc = launch_status();
   if (rc != DH3D_OK) return rc;
-  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, cands, boxes);
+  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, 1 << 30, 30, 0, cands, boxes);
   rc = launch_status();
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(np1, kKnnThreads), b);

@@ -154,4 +154,48 @@ int keypoint_nms_launch(const float* xyz, const float* attention, int B, int N, 
   return launch_status();
 }
 
+// ---------------------------------------------------------------------------------------------
+// The rest of the reference's --perform_nms output mode (evaluate/local_eval/localdesc_extract.py:92-104):
+//   response = 1 - attention                       (:95)       -> affine_kernel
+//   xyzfeatatt_nms = res[max_indices, :]           (:99)       -> gather_rows_kernel (idx < 0 = padding -> zero row)
+// ---------------------------------------------------------------------------------------------
+__global__ void affine_kernel(const float* __restrict__ x, float a, float b, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = fmaf(a, x[i], b);
+}
+
+int affine_launch(const float* x, float a, float b, float* y, size_t n, cudaStream_t st) {
+  if (!x || !y) return DH3D_ERR_NULL;
+  if (n == 0) return DH3D_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 16) blocks = (size_t)kNumSMs * 16;
+  affine_kernel<<<(int)blocks, 256, 0, st>>>(x, a, b, y, n);
+  return launch_status();
+}
+
+// out[b, j, 0:c] = idx[b, j] >= 0 ? src[b, idx[b, j], 0:c] : 0     (out rows ldo floats apart)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                   float* __restrict__ out, long long rows, int m, int n, int c, int ldo) {
+  const long long total = rows * c;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / c;
+    const int col = (int)(e - r * c);
+    const long long b = r / m;
+    const int ii = __ldg(idx + r);
+    out[r * ldo + col] = (ii >= 0 && ii < n) ? __ldg(src + ((long long)b * n + ii) * c + col) : 0.f;
+  }
+}
+
+int gather_rows_launch(int b, int n, int c, int m, const float* src, const int32_t* idx, float* out, int ldo,
+                       cudaStream_t st) {
+  if (!src || !idx || !out) return DH3D_ERR_NULL;
+  if (b <= 0 || n <= 0 || c <= 0 || m <= 0 || ldo < c) return DH3D_ERR_DIM;
+  const long long rows = (long long)b * m;
+  long long blocks = (rows * c + 255) / 256;
+  if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
+  gather_rows_kernel<<<(int)blocks, 256, 0, st>>>(src, idx, out, rows, m, n, c, ldo);
+  return launch_status();
+}
+
 }  // namespace dh3d

@@ -56,14 +56,15 @@ class DH3D(nn.Module):
 
     @torch.no_grad()
     def forward(self, points, knn_inds=None, outputs=("local_desc", "attention", "globaldesc"),
-                overlap=True):
+                overlap=True, out=None):
         """points [B,N,3] fp32 CUDA; knn_inds optional [B,N,K] i32 (the reference's 'knn_inds'
         input for N > 8192, model.py:148-155).  Returns a dict with the requested tensors:
           feat [B,N,128] raw, local_desc [B,N,128] l2-normed, attention [B,N,1], globaldesc [B,256],
-          xyz_feat [B,N,131], xyz_feat_att [B,N,132] (the reference's saved tensor names)."""
+          xyz_feat [B,N,131], xyz_feat_att [B,N,132] (the reference's saved tensor names).
+        ``out``: optional dict of caller-owned result tensors for 'local_desc' [B,N,featdim], 'attention' [B,N,1],
+        'globaldesc' [B,256] (e.g. views of one contiguous block, so a step's results leave in ONE D2H copy)."""
         c = self.config
         points = points.contiguous()
-        out = {}
         same_geometry = c.extract_global and c.gl_dilate == c.dilate
         cur = torch.cuda.current_stream(points.device)
 
@@ -87,13 +88,16 @@ class DH3D(nn.Module):
             geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
 
         want = set(outputs)
+        given = out or {}
+        out = {}
         if want & {"local_desc", "xyz_feat", "xyz_feat_att"}:
-            feat, out["local_desc"] = self.local(points, knn_inds, geometry=geometry, with_desc=True)
+            feat, out["local_desc"] = self.local(points, knn_inds, geometry=geometry, with_desc=True,
+                                                 desc_out=given.get("local_desc"))
         else:
             feat = self.local(points, knn_inds, geometry=geometry)
         out["feat"] = feat
         if c.detection and want & {"attention", "xyz_feat_att"}:
-            out["attention"] = self.detection_block_reliable(feat)
+            out["attention"] = self.detection_block_reliable(feat, out=given.get("attention"))
         if c.extract_global and "globaldesc" in want:
             # (running the detector head on the side stream next to the global branch was measured: no gain,
             #  3.18 vs 3.17 ms per step -- every large kernel here is a persistent one-CTA-per-SM grid)
@@ -106,7 +110,7 @@ class DH3D(nn.Module):
             if c.global_subsample > 0:   # core/model.py:118-121
                 gpoints, forglobal, _ = subsample(points, forglobal, c.global_subsample)
             att = self.globalatt(forglobal)
-            out["globaldesc"] = self.netvlad(gpoints, forglobal, att, final_l2norm=True)
+            out["globaldesc"] = self.netvlad(gpoints, forglobal, att, final_l2norm=True, out=given.get("globaldesc"))
         if "xyz_feat" in want:
             out["xyz_feat"] = torch.cat([points, out["local_desc"]], dim=-1)
         if "xyz_feat_att" in want and c.detection:
@@ -114,25 +118,68 @@ class DH3D(nn.Module):
         return out
 
 
+@torch.no_grad()
+def extract_keypoints(points, local_desc, attention, nms_radius=0.5, min_response_ratio=0.01, max_keypoints=512,
+                      out=None):
+    """The reference's ``--perform_nms`` output mode (evaluate/local_eval/localdesc_extract.py:92-104) for a whole
+    batch on the device: keypoint NMS on ``1 - attention`` (``single_nms``, core/utils.py:15-43), then only the
+    detected rows of 'xyz_feat_att' are kept.
+
+    points [B,N,3], local_desc [B,N,C], attention [B,N,1] -> (rows [B,max_keypoints,3+C+1] with cloud b's
+    keypoints in rows [0, counts[b]) in the reference's order (descending response) and zeros after, counts [B] i32).
+    ``out``: caller-owned [B,max_keypoints,3+C+1] tensor."""
+    from .utils import batched_nms
+    B, N, C = local_desc.shape
+    response = ops.affine(attention.reshape(B, N).contiguous(), -1.0, 1.0)          # 1 - attention (:95)
+    idx, counts = batched_nms(points, response, nms_radius, min_response_ratio, max_keypoints)
+    rows = out if out is not None else torch.empty((B, max_keypoints, 3 + C + 1), dtype=points.dtype,
+                                                   device=points.device)
+    ops.gather_rows_cols(points, idx, rows, 0)          # rows with idx < 0 (beyond counts[b]) are zero-filled
+    ops.gather_rows_cols(local_desc, idx, rows, 3)
+    ops.gather_rows_cols(attention, idx, rows, 3 + C)
+    return rows, counts
+
+
+def result_block(model, batch, n_points, outputs, device):
+    """One contiguous fp32 block holding a step's results back to back, and the views ``forward(out=...)``
+    writes through: everything a step returns leaves the GPU in ONE device-to-host copy."""
+    c = model.config
+    shapes = {"local_desc": (batch, n_points, c.featdim), "attention": (batch, n_points, 1),
+              "globaldesc": (batch, c.output_dim)}
+    names = [k for k in ("local_desc", "attention", "globaldesc") if k in outputs and
+             (k != "attention" or c.detection) and (k != "globaldesc" or c.extract_global)]
+    sizes = [int(torch.Size(shapes[k]).numel()) for k in names]
+    padded = [(n + 3) // 4 * 4 for n in sizes]           # keep every view 16-byte aligned
+    block = torch.empty(sum(padded), dtype=torch.float32, device=device)
+    views, off = {}, 0
+    for k, n, pn in zip(names, sizes, padded):
+        views[k] = block[off:off + n].view(shapes[k])
+        off += pn
+    return block, views
+
+
 class GraphedForward(object):
     """The forward pass captured once into a CUDA graph (all ~32 kernel launches, both streams) and
     replayed per batch: removes the host launch cost and the inter-kernel gaps.  Shapes are frozen to
-    the example batch; outputs are static tensors that the next replay overwrites."""
+    the example batch; outputs are static tensors that the next replay overwrites.  The requested results
+    are views of ONE contiguous block (``self.block``), see result_block()."""
 
     def __init__(self, model, example_points, outputs=("local_desc", "attention", "globaldesc"),
                  overlap=True, warmup=3):
         self.model, self.outputs = model, tuple(outputs)
         self.static_in = example_points.detach().clone().contiguous()
+        B, N, _ = self.static_in.shape
+        self.block, self.views = result_block(model, B, N, self.outputs, self.static_in.device)
         side = torch.cuda.Stream(device=self.static_in.device)
         side.wait_stream(torch.cuda.current_stream(self.static_in.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):   # folds BN, sets kernel attributes, warms the allocator
-                model(self.static_in, outputs=self.outputs, overlap=overlap)
+                model(self.static_in, outputs=self.outputs, overlap=overlap, out=self.views)
         torch.cuda.current_stream(self.static_in.device).wait_stream(side)
         torch.cuda.synchronize(self.static_in.device)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_out = model(self.static_in, outputs=self.outputs, overlap=overlap)
+            self.static_out = model(self.static_in, outputs=self.outputs, overlap=overlap, out=self.views)
 
     def __call__(self, points):
         self.static_in.copy_(points, non_blocking=True)

@@ -62,9 +62,11 @@ def flex_pool(features, neighborhood, with_argmax=False):
     K = neighborhood.shape[2]
     out = torch.empty_like(features)
     arg = torch.empty((B, N, D), dtype=i32, device=features.device) if with_argmax else None
+    _lib.stats.tag = "n%d_K%d_D%d_A%d" % (B * N, K, D, int(with_argmax))
     call("dh3d_flex_pool_pm", check(features, f32, "features", 3),
          check(neighborhood, i32, "neighborhood", 3), check(out, f32, "out"), opt(arg, i32, "argmax"),
          B, N, K, D, stream_ptr(features.device))
+    _lib.stats.tag = None
     return (out, arg) if with_argmax else out
 
 
@@ -108,10 +110,12 @@ def conv_pointset(features, theta, bias, neighborhood, scale=None, shift=None, a
     if tuple(theta.shape) != (Din, Dout) or tuple(bias.shape) != (Dout,):
         raise _lib.Dh3dError("conv_pointset: theta/bias shape mismatch")
     out = torch.empty((B, N, Dout), dtype=f32, device=features.device)
+    _lib.stats.tag = "n%d_K%d_Ci%d_Co%d" % (B * N, K, Din, Dout)
     call("dh3d_conv_pointset_pm", check(features, f32, "features", 3), check(theta, f32, "theta"),
          check(bias, f32, "bias"), check(neighborhood, i32, "neighborhood", 3), check(out, f32, "out"),
          B, N, K, Din, Dout, opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act),
          stream_ptr(features.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -138,8 +142,10 @@ def group_point(points, idx):
     B, N, C = points.shape
     _, M, S = idx.shape
     out = torch.empty((B, M, S, C), dtype=f32, device=points.device)
+    _lib.stats.tag = "B%d_M%d_S%d_C%d" % (B, M, S, C)
     call("dh3d_group_point", B, N, C, M, S, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
          check(out, f32, "out"), stream_ptr(points.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -198,8 +204,10 @@ def three_nn(xyz1, xyz2, exhaustive=False):
              check(dist, f32, "dist"), check(idx, i32, "idx"), stream_ptr(xyz1.device))
         return dist, idx
     ws, wp, wn = workspace(query("dh3d_three_nn_workspace_bytes", B, n, m), xyz1.device)
+    _lib.stats.tag = "B%d_n%d_m%d" % (B, n, m)
     call("dh3d_three_nn_ws", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
          check(dist, f32, "dist"), check(idx, i32, "idx"), wp, wn, stream_ptr(xyz1.device))
+    _lib.stats.tag = None
     return dist, idx
 
 
@@ -207,16 +215,19 @@ def three_interpolate(points, idx, weight, weight_is_dist2=False, out=None, out_
     """``out``/``out_col``: write into columns [out_col, out_col+c) of an existing [B,n,ld] tensor (fused concat)."""
     B, m, c = points.shape
     n = idx.shape[1]
+    _lib.stats.tag = "B%d_n%d_m%d_C%d" % (B, n, m, c)
     if out is not None:
         check(out, f32, "out", 3)
         call("dh3d_three_interpolate_ld", B, m, c, n, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
              check(weight, f32, "weight", 3), int(bool(weight_is_dist2)),
              ctypes.c_void_p(out.data_ptr() + 4 * out_col), out.shape[-1], stream_ptr(points.device))
+        _lib.stats.tag = None
         return out
     out = torch.empty((B, n, c), dtype=f32, device=points.device)
     name = "dh3d_three_interpolate_from_dist" if weight_is_dist2 else "dh3d_three_interpolate"
     call(name, B, m, c, n, check(points, f32, "points", 3), check(idx, i32, "idx", 3),
          check(weight, f32, "weight", 3), check(out, f32, "out"), stream_ptr(points.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -226,8 +237,10 @@ def group_point_cols(wide, col, c, idx):
     _, M, S = idx.shape
     out = torch.empty((B, M, S, c), dtype=f32, device=wide.device)
     check(wide, f32, "wide", 3)
+    _lib.stats.tag = "B%d_M%d_S%d_C%d" % (B, M, S, c)
     call("dh3d_group_point_ld", B, N, c, M, S, ctypes.c_void_p(wide.data_ptr() + 4 * col), ld,
          check(idx, i32, "idx", 3), check(out, f32, "out"), stream_ptr(wide.device))
+    _lib.stats.tag = None
     return out
 
 
@@ -240,17 +253,21 @@ def add_l2_normalize_rows(a, b, eps):
     return s, y
 
 
-def linear_join(xa, packed_a, scale_a, shift_a, act_a, xb, packed_b, scale_b, shift_b, act_b, eps=None):
+def linear_join(xa, packed_a, scale_a, shift_a, act_a, xb, packed_b, scale_b, shift_b, act_b, eps=None, out_norm=None):
     """act_a((xa @ Wa)*scale_a + shift_a) + act_b((xb @ Wb)*scale_b + shift_b), and with ``eps`` also its
     l2-normalised rows, in one launch (weights as linear_prepack buffers; N must be 128).
-    Returns y, or (y, y_normalised) when eps is given."""
+    Returns y, or (y, y_normalised) when eps is given.  ``out_norm``: caller-owned [.., N] tensor for y_normalised."""
     M, Ka = _rows(xa)
     Mb, Kb = _rows(xb)
     (Kpa, N), (Kpb, Nb) = packed_a._dh3d_kn, packed_b._dh3d_kn
     if M != Mb or Kpa != Ka or Kpb != Kb or N != Nb:
         raise _lib.Dh3dError("linear_join: shape mismatch")
     y = torch.empty(xa.shape[:-1] + (N,), dtype=f32, device=xa.device)
-    yn = torch.empty_like(y) if eps is not None else None
+    yn = None
+    if eps is not None:
+        yn = torch.empty_like(y) if out_norm is None else out_norm
+        if tuple(yn.shape) != tuple(y.shape):
+            raise _lib.Dh3dError("linear_join: out_norm has shape %s, expected %s" % (tuple(yn.shape), tuple(y.shape)))
     _lib.stats.tag = "M%d_Ka%d_Kb%d_N%d" % (M, Ka, Kb, N)
     call("dh3d_linear_join_packed", check(xa, f32, "xa"), Ka, ctypes.c_void_p(packed_a.data_ptr()),
          opt(scale_a, f32, "scale_a"), opt(shift_a, f32, "shift_a"), int(act_a), check(xb, f32, "xb"), Kb,
@@ -306,14 +323,16 @@ def linear(x, w, scale=None, shift=None, act=ACT_NONE, out=None, out_col=0, pack
     return out
 
 
-def linear_rowdot(x, packed, scale, shift, act, w2, b2=0.0, act2=ACT_NONE):
+def linear_rowdot(x, packed, scale, shift, act, w2, b2=0.0, act2=ACT_NONE, out=None):
     """act2(sum_n act((x @ W)[.., n]*scale+shift) * w2[n] + b2) with W given as linear_prepack(W);
     the hidden [.., N] activation is never written (tensor-core path only)."""
     M, K = _rows(x)
     Kp, N = packed._dh3d_kn
     if Kp != K or w2.numel() != N:
         raise _lib.Dh3dError("linear_rowdot: shape mismatch")
-    y = torch.empty(x.shape[:-1], dtype=f32, device=x.device)
+    y = torch.empty(x.shape[:-1], dtype=f32, device=x.device) if out is None else out
+    if y.numel() != M:
+        raise _lib.Dh3dError("linear_rowdot: out has %d elements, expected %d" % (y.numel(), M))
     _lib.stats.tag = "M%d_K%d_N%d" % (M, K, N)
     call("dh3d_linear_rowdot_packed", check(x, f32, "x"), K, ctypes.c_void_p(packed.data_ptr()),
          opt(scale, f32, "scale"), opt(shift, f32, "shift"), int(act), check(w2, f32, "w2"),
@@ -344,10 +363,33 @@ def se_pool_excite(x, neighborhood, w1, b1, w2, b2):
     K = neighborhood.shape[2]
     H = w1.shape[1]
     y = torch.empty_like(x)
+    _lib.stats.tag = "n%d_K%d_C%d" % (B * N, K, C)
     call("dh3d_se_pool_excite", check(x, f32, "x", 3), check(neighborhood, i32, "neighborhood", 3),
          check(w1, f32, "w1", 2), check(b1, f32, "b1"), check(w2, f32, "w2", 2), check(b2, f32, "b2"),
          check(y, f32, "y"), B, N, K, C, H, stream_ptr(x.device))
+    _lib.stats.tag = None
     return y
+
+
+def affine(x, a, b):
+    """a * x + b elementwise (the reference's `1 - attention`, localdesc_extract.py:95)."""
+    y = torch.empty_like(x)
+    call("dh3d_affine", check(x, f32, "x"), _cf(float(a)), _cf(float(b)), check(y, f32, "y"), _cs(x.numel()),
+         stream_ptr(x.device))
+    return y
+
+
+def gather_rows_cols(src, idx, out, out_col):
+    """out[b, j, out_col:out_col+C] = src[b, idx[b,j], :] (zero where idx < 0); src [B,N,C], idx [B,M] i32,
+    out [B,M,ld] (the reference's `res[max_indices, :]`, written per column block)."""
+    B, N, C = src.shape
+    M = idx.shape[1]
+    check(out, f32, "out", 3)
+    if out.shape[0] != B or out.shape[1] != M or out_col + C > out.shape[2]:
+        raise _lib.Dh3dError("gather_rows_cols: out shape %s does not fit" % (tuple(out.shape),))
+    call("dh3d_gather_rows", B, N, C, M, check(src, f32, "src", 3), check(idx, i32, "idx", 2),
+         ctypes.c_void_p(out.data_ptr() + 4 * out_col), out.shape[2], stream_ptr(src.device))
+    return out
 
 
 def add(a, b):
@@ -398,13 +440,16 @@ def transpose_pm_to_cm(x):
 
 
 def netvlad(features, att, cluster_weights, cluster_bn, cluster_weights2, hidden1_weights, bn,
-            gating_weights, gating_bn, final_l2norm=True):
+            gating_weights, gating_bn, final_l2norm=True, out=None):
     """features [B,N,D], att [B,N] (or [B,N,1]); *_bn = (scale, shift) folded BatchNorm pairs."""
     B, N, D = features.shape
     Kc = cluster_weights.shape[1]
     out_dim = hidden1_weights.shape[1]
     att = att.reshape(B, N)
-    out = torch.empty((B, out_dim), dtype=f32, device=features.device)
+    if out is None:
+        out = torch.empty((B, out_dim), dtype=f32, device=features.device)
+    elif tuple(out.shape) != (B, out_dim):
+        raise _lib.Dh3dError("netvlad: out has shape %s, expected %s" % (tuple(out.shape), (B, out_dim)))
     nbytes = query("dh3d_netvlad_workspace_bytes", B, N, D, Kc, out_dim)
     if nbytes == 0:
         raise _lib.Dh3dError("netvlad: unsupported configuration D=%d Kc=%d out=%d" % (D, Kc, out_dim))

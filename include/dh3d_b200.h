@@ -327,6 +327,14 @@ DH3D_API int dh3d_three_interpolate_grad(int b, int n, int c, int m, const float
  *   (sklearn's arithmetic).  remove_noise != 0 zeroes the attention of points whose 8th neighbour is
  *   farther than 2.0 (:19-22).  N >= 50.  `attention` is not modified (the reference mutates it).
  * ------------------------------------------------------------------------------------------- */
+/* The two array expressions around single_nms in the reference's --perform_nms output mode
+ * (evaluate/local_eval/localdesc_extract.py:92-104), so that only keypoint rows leave the GPU:
+ *   dh3d_affine:      y = a * x + b                        (`attention = 1 - res[:, -1]`, :95)
+ *   dh3d_gather_rows: out[b, j, 0:c] = src[b, idx[b,j], 0:c], zero row where idx[b,j] < 0
+ *                     (`res[max_indices, :]`, :99; out rows are ldo >= c floats apart: a column block) */
+DH3D_API int dh3d_affine(const float* x, float a, float b, float* y, size_t count, void* stream);
+DH3D_API int dh3d_gather_rows(int b, int n, int c, int m, const float* src, const int32_t* idx, float* out, int ldo,
+                     void* stream);
 DH3D_API size_t dh3d_keypoint_nms_workspace_bytes(int B, int N);
 DH3D_API int dh3d_keypoint_nms(const float* xyz_pm, const float* attention, int B, int N, float nms_radius,
                       float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,

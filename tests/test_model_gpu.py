@@ -9,6 +9,15 @@ from conftest import make_cloud
 pytestmark = pytest.mark.gpu
 
 
+# Tolerances of the assembled forward at the benchmark shape, per output: max |err| / rms(expected) against the
+# fp64 oracle composition.  north_star's 1e-4 is the per-op bar; the forward chains ~20 fp32 layers.  Measured on
+# B200 (profiles/parity_r2a.txt; random / duplicate-padded / all-zero cloud): feat 0.93e-4 / 1.13e-4 / 0.06e-4 (the
+# un-normalised 128-D sum of two ReLU branches: its MAX error over 1 M elements sits at ~1.1 sigma-of-the-max above
+# the per-op bar), local_desc 2.1e-5, attention 8.8e-6, globaldesc 6.8e-7.  Every NORMALISED output the reference's
+# extractors save (xyz_feat, xyz_feat_att, globaldesc) is therefore held to 1e-4; raw `feat` to 2e-4.
+FWD_TOL = {"feat": 2e-4, "local_desc": 1e-4, "attention": 1e-4, "globaldesc": 1e-4}
+
+
 def _model(seed=0):
     from dh3d_b200.configs import full_config
     from dh3d_b200.model import DH3D, init_random_
@@ -25,18 +34,15 @@ def _rel_err(a, e):
 
 def test_full_forward_matches_oracle_small():
     """N=1024 (M=128), B=2.  The oracle recomputes FPS/kNN/3-NN per block like the reference graph
-    and runs the dense math in fp64; the chained fp32 pipeline must stay within 1e-3 of it at the
-    deep outputs (per-op parity is held to 1e-4 in test_ops_gpu.py; ~20 chained fp32 layers
-    compound it)."""
+    and runs the dense math in fp64; tolerances per output: FWD_TOL below (1e-4 on every normalised
+    output, 2e-4 on the raw feature sum)."""
     from oracle import net
     model, params = _model()
     pts = make_cloud(np.random.RandomState(0), 2, 1024, extent=10.0)
     out = model(torch.from_numpy(pts).cuda(), outputs=("local_desc", "attention", "globaldesc", "xyz_feat_att"))
     exp = net.forward(pts, params)
-    assert _rel_err(out["feat"], exp["feat"]) < 1e-3
-    assert _rel_err(out["local_desc"], exp["local_desc"]) < 1e-3
-    assert _rel_err(out["attention"], exp["attention"]) < 1e-3
-    assert _rel_err(out["globaldesc"], exp["globaldesc"]) < 1e-3
+    for k, tol in FWD_TOL.items():
+        assert _rel_err(out[k], exp[k]) < tol, (k, _rel_err(out[k], exp[k]))
     xfa = out["xyz_feat_att"]
     assert xfa.shape == (2, 1024, 3 + 128 + 1)
     assert torch.equal(xfa[..., :3].cpu(), torch.from_numpy(pts))
@@ -113,14 +119,6 @@ def test_unfused_composition_paths_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
                         "matches_oracle_small or full_size_properties"], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
-# Tolerances of the assembled forward at the benchmark shape, per output (max |err| / rms(expected) against the
-# fp64 oracle composition).  north_star's 1e-4 is the PER-OP bar (held in test_ops_gpu.py / test_sweep_gpu.py);
-# the forward chains ~20 fp32 layers, each contributing its own <= 1e-4 * rms rounding, which adds in quadrature
-# to a few 1e-4 at the deep outputs.  scripts/parity_report.py prints the measured values per layer
-# (profiles/parity_r2*.txt).
-FWD_TOL = {"feat": 3e-4, "local_desc": 3e-4, "attention": 3e-4, "globaldesc": 3e-4}
 
 
 def _benchmark_shape_clouds():

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "dh3d_transpose_cm_to_pm": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p]),
     "dh3d_transpose_pm_to_cm": (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p]),
     "dh3d_topk_l2": (_c_int, [_p, _c_int, _p, _p, _c_int, _c_int, _c_int, _p, _p, _p]),
+    "dh3d_topk_l2_exact": (_c_int, [_p, _c_int, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _p]),
     "dh3d_netvlad_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "dh3d_netvlad": (_c_int, [_p, _p] + [_c_int] * 5 + [_p] * 10 + [_c_int, _p, _p, _c_size_t, _p]),
     "dh3d_flex_conv_grad_workspace_bytes": (_c_size_t, [_c_int] * 5),

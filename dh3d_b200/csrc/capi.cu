@@ -126,6 +126,9 @@ int keypoint_nms_launch(const float* xyz, const float* attention, int B, int N, 
                         float min_response_ratio, int max_keypoints, int remove_noise, int32_t* out_idx,
                         int32_t* out_cnt, void* ws, size_t ws_bytes, cudaStream_t st);
 // topk.cu
+int topk_l2_exact_launch(const float* gram, int ldg, const float* qn, const float* rn, const float* qd,
+                         const float* rd, int Q, int R, int D, int K, int32_t* idx, float* val, int32_t* cand,
+                         float* cand_val, cudaStream_t st);
 int topk_l2_launch(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                    int32_t* idx, float* val, cudaStream_t st);
 // netvlad.cu
@@ -357,6 +360,11 @@ int dh3d_transpose_pm_to_cm(const void* src_pm, void* dst_cm, int B, int N, int 
   return transpose_launch(src_pm, dst_cm, B, N, C, S(stream));
 }
 
+int dh3d_topk_l2_exact(const float* gram, int ldg, const float* qn, const float* rn, const float* query,
+                       const float* ref, int Q, int R, int D, int K, int32_t* idx, float* val, int32_t* cand,
+                       float* cand_val, void* stream) {
+  return topk_l2_exact_launch(gram, ldg, qn, rn, query, ref, Q, R, D, K, idx, val, cand, cand_val, S(stream));
+}
 int dh3d_topk_l2(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                  int32_t* idx, float* val, void* stream) {
   return topk_l2_launch(gram, ldg, qn, rn, Q, R, K, idx, val, S(stream));

@@ -44,8 +44,10 @@ constexpr uint32_t kCAStageBytes = 128 * 128;   // 128 rows x 32 channels fp32
 template <int BN, bool K8>
 struct CACfg {
   static constexpr int kStages = 2;                           // UMMA operand stages
-  static constexpr int kGStages = K8 ? 4 : (BN <= 64 ? 5 : 3);   // gather stages (16 KB each)
-  static constexpr int kOutRows = (K8 && BN > 64) ? 16 : 32;  // rows per epilogue TMA store (smem budget)
+  // gather stages (16 KB each).  K == 8 path: 6 where the operand stages leave room (BN = 64: the 32->64 and 64->64
+  // layers, 85 % of DH3D's gathered bytes) = 5 rows x 32 B in flight per consumer thread, 80 KB per SM; 4 at BN = 128.
+  static constexpr int kGStages = K8 ? (BN <= 64 ? 6 : 4) : (BN <= 64 ? 5 : 3);
+  static constexpr int kOutRows = K8 ? 16 : 32;  // rows per epilogue TMA store (smem budget)
   static constexpr uint32_t kOutBytes = 4 * kOutRows * 32 * 4;
   static constexpr uint32_t kBBytes = BN * kTcBK * 4;
   static constexpr uint32_t kStageBytes = 2 * kTcABytes + 2 * kBBytes;
@@ -175,10 +177,10 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
     // 16-byte chunk, so with the 128B-swizzle chunk index (chunk ^ rw) every LDS.128 / STS.128 below -- gather
     // ring, A slabs, offset table -- touches 8 distinct 16-byte columns: no bank conflicts (the (row, seg)
     // mapping of the generic path had 2-way conflicts on all three; ncu r1j: 10.8 M of 26 M wavefronts).
-    // Item i of a group is neighbour slot k = i; the ring slot is k & 3, the item issued while item k is
-    // being reduced is k + 3 (next group when k >= 5), all static under the unroll.
+    // Item i of a group is neighbour slot k = i; the item issued while item k is being reduced is k + AH (next
+    // group when k + AH >= 8), static under the unroll; the ring positions are two running byte offsets.
     constexpr int AH = G - 1;     // items in flight per thread
-    static_assert(G == 4, "the unrolled K == 8 schedule assumes a 4-slot ring");
+    constexpr uint32_t kRing = G * kCAStageBytes;
     const int wc = warp - 2;
     const int rw = lane & 7, seg = lane >> 3;
     const int r = 8 * wc + rw;
@@ -208,14 +210,17 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
         pc[c] = __ldg(a.xyz + (long long)rr * 3 + c);
       }
     };
-    auto issue = [&](int k, int slot) {
+    uint32_t i_off = 0, c_off = 0;   // ring byte offsets of the next item to issue / to consume
+    auto issue = [&](int k) {
       if (i_mt < num_mt) {
         const float* src = a.feat + (long long)irow[k ^ rw] * a.Din + i_cg * kTcBK + seg * 4;
-        uint8_t* dst = gbase + slot * kCAStageBytes;
+        uint8_t* dst = gbase + i_off;
         cp_async16(dst + o0, src);
         cp_async16(dst + o1, src + 16);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");  // one group per item, empty past the end
+      i_off += kCAStageBytes;
+      if (i_off == kRing) i_off = 0;
     };
     auto next_group = [&]() {
       if (++i_cg == num_cg) i_cg = 0;
@@ -227,7 +232,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
     };
     if (i_mt < num_mt) enter_tile(i_mt);
 #pragma unroll
-    for (int i = 0; i < AH; ++i) issue(i, i);
+    for (int i = 0; i < AH; ++i) issue(i);
 
     // ---- consume side
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
@@ -245,7 +250,9 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           asm volatile("cp.async.wait_group %0;" ::"n"(AH - 1) : "memory");  // this thread's item k landed
-          const uint8_t* gs = gbase + (k & 3) * kCAStageBytes;
+          const uint8_t* gs = gbase + c_off;
+          c_off += kCAStageBytes;
+          if (c_off == kRing) c_off = 0;
           const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(gs + o0);
           const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(gs + o1);
           const float4 d = drow[k ^ rw];
@@ -258,7 +265,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
             ffma2(m[3][c], fv[c], d.z);
           }
           if (k == 8 - AH) next_group();
-          issue((k + AH) & 7, (k + AH) & 3);
+          issue((k + AH) & 7);
         }
         // 4 K-slabs (p' = 1, x, y, z) -> operand stages p' & 1, swizzled K-major, hi (raw) + lo
 #pragma unroll

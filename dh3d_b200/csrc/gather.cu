@@ -662,12 +662,55 @@ __global__ void conv_pointset_cm_kernel(const float* __restrict__ feat, const fl
   }
 }
 
+// DH3D's own shape (Din = 3 coordinates, K = 8; core/backbones.py:108): one thread per POINT gathers its K x Din
+// differences once into registers and walks the Dout outputs (theta / bias are warp-uniform loads, the [B,Dout,N]
+// stores are coalesced over n).  The kernel above re-gathers them for every output channel (Dout x the L2 requests:
+// 0.39 ms for 32 x 8192 points against 0.076 ms of the reference kernel; this form: same FMA order, ~10x less traffic).
+template <int DIN, int KK>
+__global__ void __launch_bounds__(256)
+conv_pointset_cm_point_kernel(const float* __restrict__ feat, const float* __restrict__ theta,
+                              const float* __restrict__ bias, const int32_t* __restrict__ nbr,
+                              float* __restrict__ out, int B, int N, int Dout) {
+  const long long total = (long long)B * N;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(e % N);
+    const int b = (int)(e / N);
+    const float* f = feat + (long long)b * DIN * N;
+    const int32_t* nb = nbr + (long long)b * KK * N + n;
+    const int n0 = __ldg(nb);
+    float base[DIN], diff[KK][DIN];
+#pragma unroll
+    for (int c = 0; c < DIN; ++c) base[c] = __ldg(f + (long long)c * N + n0);
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const int g = __ldg(nb + (long long)k * N);
+#pragma unroll
+      for (int c = 0; c < DIN; ++c) diff[k][c] = __fsub_rn(__ldg(f + (long long)c * N + g), base[c]);
+    }
+    float* o_ptr = out + (long long)b * Dout * N + n;
+    for (int o = 0; o < Dout; ++o) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < KK; ++k)
+#pragma unroll
+        for (int c = 0; c < DIN; ++c) acc = __fmaf_rn(__ldg(theta + c * Dout + o), diff[k][c], acc);
+      o_ptr[(long long)o * N] = __fadd_rn(acc, __ldg(bias + o));
+    }
+  }
+}
+
 int conv_pointset_cm_launch(const float* feat, const float* theta, const float* bias,
                             const int32_t* nbr, float* out, int B, int N, int K, int Din, int Dout,
                             cudaStream_t st) {
   if (!feat || !theta || !bias || !nbr || !out) return DH3D_ERR_NULL;
   if (B <= 0 || N <= 0 || K <= 0 || Din <= 0 || Dout <= 0) return DH3D_ERR_DIM;
   if (Din > 64) return DH3D_ERR_UNSUPPORTED;
+  if (Din == 3 && K == 8) {
+    conv_pointset_cm_point_kernel<3, 8><<<ew_blocks((long long)B * N, 256), 256, 0, st>>>(feat, theta, bias, nbr, out,
+                                                                                       B, N, Dout);
+    return launch_status();
+  }
   conv_pointset_cm_kernel<<<ew_blocks((long long)B * Dout * N, 256), 256, 0, st>>>(
       feat, theta, bias, nbr, out, B, N, K, Din, Dout);
   return launch_status();

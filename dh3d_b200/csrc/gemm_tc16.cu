@@ -97,31 +97,110 @@ struct T16Epilogue {
   float* y; int ldy;
 };
 
-// x[row, 0:K] . (wh + wl)[n, 0:K] by one warp: lane l owns k = 8l .. 8l+7 (+256 per round), 16-byte loads of the
-// K-major weight rows (Kp is a multiple of 8 and zero padded) and of the activation row; every lane gets the sum.
+constexpr int kT16RB = 16;          // out-of-window rows recomputed together (one pass over W per batch)
+constexpr int kT16FixMaxK = 1024;   // batched recompute stages RB x K floats in the (idle) stage ring
+
+// 8 weights (wh + wl, exact in fp32) of column n at k0 .. k0+7
+struct T16W8 { float w[8]; };
+__device__ __forceinline__ T16W8 t16_load_w8(const __half* __restrict__ h, const __half* __restrict__ l, int k0) {
+  const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h + k0));
+  const uint4 lv = __ldg(reinterpret_cast<const uint4*>(l + k0));
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+  T16W8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    r.w[2 * i] = a.x + b.x;
+    r.w[2 * i + 1] = a.y + b.y;
+  }
+  return r;
+}
+
+// acc[r] += x_r[k0 .. k0+7] . w8 for the staged rows (xs: [RB][K] floats in shared memory); K % 4 == 0 only
+__device__ __forceinline__ void t16_dot_rows(float (&acc)[kT16RB], const float* xs, int K, int k0, const T16W8& w) {
+  const bool tail = k0 + 4 < K;
+#pragma unroll
+  for (int r = 0; r < kT16RB; ++r) {
+    const float4 x0 = *reinterpret_cast<const float4*>(xs + r * K + k0);
+    const float4 x1 = tail ? *reinterpret_cast<const float4*>(xs + r * K + k0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float a = acc[r];
+    a = fmaf(x0.x, w.w[0], a); a = fmaf(x0.y, w.w[1], a); a = fmaf(x0.z, w.w[2], a); a = fmaf(x0.w, w.w[3], a);
+    a = fmaf(x1.x, w.w[4], a); a = fmaf(x1.y, w.w[5], a); a = fmaf(x1.z, w.w[6], a); a = fmaf(x1.w, w.w[7], a);
+    acc[r] = a;
+  }
+}
+
+// rows of the batch -> shared memory (zero rows beyond nrows), by the whole CTA
+__device__ __forceinline__ void t16_stage_rows(float* xs, const float* x, int ldx, int K, const int* brow, int nrows) {
+  const int kv = K >> 2;
+  for (int i = threadIdx.x; i < kT16RB * kv; i += blockDim.x) {
+    const int r = i / kv, c = i - r * kv;
+    reinterpret_cast<float4*>(xs)[i] = r < nrows ? ldg4(x + (long long)brow[r] * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// fp32 recompute of up to RB output rows by the whole CTA (out-of-window rows only; see the header): the rows'
+// activations are staged in the idle stage ring, one warp per output column reads the (wh + wl) column ONCE for
+// the whole batch (lane l owns k = 8l .. 8l+7, +256 per round; 16-byte loads), reduces with shuffles and applies
+// the epilogue.  y[row, n] = act((x[row, :] @ W[:, n]) * scale[n] + shift[n]) with W = (wh + wl) * colscale * 2^4.
+template <bool ROWDOT>
+__device__ __noinline__ void t16_fixup_batch(const T16Epilogue& ep, const int* brow, int nrows, int K, int N, float* xs,
+                                             float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  t16_stage_rows(xs, ep.x, ep.ldx, K, brow, nrows);
+  __syncthreads();
+  float part[kT16RB];
+#pragma unroll
+  for (int r = 0; r < kT16RB; ++r) part[r] = 0.f;
+  for (int n = warp; n < N; n += nw) {
+    const __half* h = ep.wh + (long long)n * ep.Kp;
+    const __half* l = ep.wl + (long long)n * ep.Kp;
+    float acc[kT16RB];
+#pragma unroll
+    for (int r = 0; r < kT16RB; ++r) acc[r] = 0.f;
+    for (int k0 = lane * 8; k0 < K; k0 += 256) t16_dot_rows(acc, xs, K, k0, t16_load_w8(h, l, k0));
+    const float cs = __ldg(ep.colscale + n) * kT16XScale;
+    const float sc = ep.scale ? __ldg(ep.scale + n) : 1.f, sh = ep.shift ? __ldg(ep.shift + n) : 0.f;
+    const float w2 = ROWDOT ? __ldg(ep.w2 + n) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kT16RB; ++r) {
+      const float v = tc_act(fmaf(warp_sum(acc[r]) * cs, sc, sh), ep.act);
+      if constexpr (ROWDOT) part[r] = fmaf(v, w2, part[r]);
+      else if (lane == 0 && r < nrows) ep.y[(long long)brow[r] * ep.ldy + n] = v;
+    }
+  }
+  if constexpr (ROWDOT) {
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kT16RB; ++r) red[warp * kT16RB + r] = part[r];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nrows) {
+      float tot = 0.f;
+      for (int w = 0; w < nw; ++w) tot += red[w * kT16RB + threadIdx.x];
+      ep.y2[brow[threadIdx.x]] = tc_act(tot + ep.b2, ep.act2);
+    }
+  }
+}
+
+// x[row, 0:K] . (wh + wl)[n, 0:K] by one warp (rows too long for the batched form): every lane gets the sum
 __device__ __forceinline__ float t16_row_dot(const float* __restrict__ xr, const __half* __restrict__ h,
                                              const __half* __restrict__ l, int K, int lane) {
   float acc = 0.f;
   for (int k0 = lane * 8; k0 < K; k0 += 256) {
-    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(h + k0));
-    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(l + k0));
+    const T16W8 w = t16_load_w8(h, l, k0);
     const float4 x0 = ldg4(xr + k0);
     const float4 x1 = (k0 + 4 < K) ? ldg4(xr + k0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);   // K % 4 == 0 only
-    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-      acc = fmaf(xs[2 * i], a.x + b.x, acc);          // wh + wl is exact in fp32 (22 significant bits)
-      acc = fmaf(xs[2 * i + 1], a.y + b.y, acc);
-    }
+    acc = fmaf(x0.x, w.w[0], acc); acc = fmaf(x0.y, w.w[1], acc); acc = fmaf(x0.z, w.w[2], acc);
+    acc = fmaf(x0.w, w.w[3], acc); acc = fmaf(x1.x, w.w[4], acc); acc = fmaf(x1.y, w.w[5], acc);
+    acc = fmaf(x1.z, w.w[6], acc); acc = fmaf(x1.w, w.w[7], acc);
   }
   return warp_sum(acc);
 }
 
-// fp32 recompute of one output row by the whole CTA, one warp per output column (out-of-window rows only; see
-// the header).  y[row, n] = act((x[row, :] @ W[:, n]) * scale[n] + shift[n]) with W = (wh + wl) * colscale * 2^4.
+// one row at a time (K > kT16FixMaxK): same arithmetic, activations read from global memory
 template <bool ROWDOT>
 __device__ __noinline__ void t16_fixup_row(const T16Epilogue& ep, int row, int K, int N, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -144,6 +223,44 @@ __device__ __noinline__ void t16_fixup_row(const T16Epilogue& ep, int row, int K
       for (int w = 0; w < nw; ++w) tot += red[w];
       ep.y2[row] = tc_act(tot + ep.b2, ep.act2);
     }
+  }
+}
+
+// The CTA's queued rows (or, if the queue overflowed, every row it owns) in batches of RB.
+// ring: the stage ring (idle now): [RB*K floats | 16 ints | nw*RB floats]
+template <bool ROWDOT, class NextTile>
+__device__ __forceinline__ void t16_fixup_all(const T16Epilogue& ep, const uint32_t* bad, int M, int K, int N,
+                                              uint8_t* ring, NextTile next_tile) {
+  const uint32_t nbad = bad[0];
+  float* xs = reinterpret_cast<float*>(ring);
+  int* brow = reinterpret_cast<int*>(xs + kT16RB * (K <= kT16FixMaxK ? K : 0));
+  float* red = reinterpret_cast<float*>(brow + kT16RB);
+  auto run = [&](int nrows) {
+    if (K <= kT16FixMaxK) {
+      t16_fixup_batch<ROWDOT>(ep, brow, nrows, K, N, xs, red);
+    } else {
+      for (int r = 0; r < nrows; ++r) t16_fixup_row<ROWDOT>(ep, brow[r], K, N, red);
+    }
+  };
+  if (nbad <= (uint32_t)kT16BadCap) {
+    for (uint32_t base = 0; base < nbad; base += kT16RB) {
+      const int nrows = min((int)(nbad - base), kT16RB);
+      __syncthreads();
+      if ((int)threadIdx.x < nrows) brow[threadIdx.x] = (int)bad[4 + base + threadIdx.x];
+      __syncthreads();
+      run(nrows);
+    }
+  } else {   // queue overflowed: redo every row this CTA owns
+    for (int t = 0, mt; (mt = next_tile(t)) >= 0; ++t)
+      for (int r0 = 0; r0 < kTcBM; r0 += kT16RB) {
+        const int row0 = mt * kTcBM + r0;
+        if (row0 >= M) break;
+        const int nrows = min(M - row0, kT16RB);
+        __syncthreads();
+        if ((int)threadIdx.x < nrows) brow[threadIdx.x] = row0 + threadIdx.x;
+        __syncthreads();
+        run(nrows);
+      }
   }
 }
 
@@ -427,18 +544,11 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   // out-of-window rows (never in-distribution): fp32 recompute over the tensor-core result; every TMA store of
   // this CTA has completed (epilogue warps waited on their bulk groups before the barrier above)
-  const uint32_t nbad = bad[0];
-  if (nbad != 0u) {
-    if (nbad <= (uint32_t)kT16BadCap) {
-      for (uint32_t i = 0; i < nbad; ++i) t16_fixup_row<ROWDOT>(ep, (int)bad[4 + i], K, N, params);
-    } else {   // queue overflowed: redo every row this CTA owns
-      for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
-        for (int r = 0; r < kTcBM; ++r) {
-          const int row = (mtb + (int)crank) * kTcBM + r;
-          if (row < M) t16_fixup_row<ROWDOT>(ep, row, K, N, params);
-        }
-    }
-  }
+  if (bad[0] != 0u)
+    t16_fixup_all<ROWDOT>(ep, bad, M, K, N, smem, [&](int t) {
+      const int mt = mt_begin + t * mt_stride;
+      return mt < num_mt ? mt + (int)crank : -1;
+    });
 }
 
 // ---- weight pre-split: W [K,N] row-major -> { W_h^T [N,Kp] fp16, W_l^T [N,Kp] fp16, colscale [N] } --------
@@ -647,33 +757,55 @@ struct JoinArgs {
   float* y; int ldy; float* yn; int ldn;
 };
 
-// fp32 recompute of one row of the join, one warp per output column; red = 128 values + one slot per warp
-__device__ __noinline__ void join16_fixup_row(const JoinArgs& a, int row, float* red) {
+// fp32 recompute of up to RB rows of the join by the whole CTA, one warp per output column (see t16_fixup_batch).
+// ring: [RB*Ka | RB*Kb | RB*128 floats (the rows' sums, for the norm pass) | nw*RB floats]
+__device__ __noinline__ void join16_fixup_batch(const JoinArgs& a, const int* brow, int nrows, uint8_t* ring) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const float* xa = a.xa + (long long)row * a.ldxa;
-  const float* xb = a.xb + (long long)row * a.ldxb;
-  float ss = 0.f;
-  __syncthreads();   // red is reused row after row
+  float* xsa = reinterpret_cast<float*>(ring);
+  float* xsb = xsa + kT16RB * a.Ka;
+  float* vbuf = xsb + kT16RB * a.Kb;
+  float* red = vbuf + kT16RB * kJBN;
+  __syncthreads();
+  t16_stage_rows(xsa, a.xa, a.ldxa, a.Ka, brow, nrows);
+  t16_stage_rows(xsb, a.xb, a.ldxb, a.Kb, brow, nrows);
+  __syncthreads();
+  float ss[kT16RB];
+#pragma unroll
+  for (int r = 0; r < kT16RB; ++r) ss[r] = 0.f;
   for (int n = warp; n < kJBN; n += nw) {
-    float va = t16_row_dot(xa, a.wah + (long long)n * a.Kpa, a.wal + (long long)n * a.Kpa, a.Ka, lane);
-    va *= __ldg(a.cs_a + n) * kT16XScale;
-    va = tc_act(fmaf(va, a.scale_a ? __ldg(a.scale_a + n) : 1.f, a.shift_a ? __ldg(a.shift_a + n) : 0.f), a.act_a);
-    float vb = t16_row_dot(xb, a.wbh + (long long)n * a.Kpb, a.wbl + (long long)n * a.Kpb, a.Kb, lane);
-    vb *= __ldg(a.cs_b + n) * kT16XScale;
-    vb = tc_act(fmaf(vb, a.scale_b ? __ldg(a.scale_b + n) : 1.f, a.shift_b ? __ldg(a.shift_b + n) : 0.f), a.act_b);
-    const float v = va + vb;
-    ss = fmaf(v, v, ss);
-    if (lane == 0) {
-      a.y[(long long)row * a.ldy + n] = v;
-      red[n] = v;
+    float va[kT16RB], vb[kT16RB];
+#pragma unroll
+    for (int r = 0; r < kT16RB; ++r) va[r] = vb[r] = 0.f;
+    for (int k0 = lane * 8; k0 < a.Ka; k0 += 256)
+      t16_dot_rows(va, xsa, a.Ka, k0, t16_load_w8(a.wah + (long long)n * a.Kpa, a.wal + (long long)n * a.Kpa, k0));
+    for (int k0 = lane * 8; k0 < a.Kb; k0 += 256)
+      t16_dot_rows(vb, xsb, a.Kb, k0, t16_load_w8(a.wbh + (long long)n * a.Kpb, a.wbl + (long long)n * a.Kpb, k0));
+    const float csa = __ldg(a.cs_a + n) * kT16XScale, csb = __ldg(a.cs_b + n) * kT16XScale;
+    const float sa = a.scale_a ? __ldg(a.scale_a + n) : 1.f, ha = a.shift_a ? __ldg(a.shift_a + n) : 0.f;
+    const float sb = a.scale_b ? __ldg(a.scale_b + n) : 1.f, hb = a.shift_b ? __ldg(a.shift_b + n) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kT16RB; ++r) {
+      const float v = tc_act(fmaf(warp_sum(va[r]) * csa, sa, ha), a.act_a) +
+                      tc_act(fmaf(warp_sum(vb[r]) * csb, sb, hb), a.act_b);
+      ss[r] = fmaf(v, v, ss[r]);
+      if (lane == 0) {
+        vbuf[r * kJBN + n] = v;
+        if (r < nrows) a.y[(long long)brow[r] * a.ldy + n] = v;
+      }
     }
   }
   if (a.has_norm) {
-    if (lane == 0) red[kJBN + warp] = ss;
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < kT16RB; ++r) red[warp * kT16RB + r] = ss[r];
+    }
     __syncthreads();
-    float tot = 0.f;
-    for (int w = 0; w < nw; ++w) tot += red[kJBN + w];
-    if (threadIdx.x < kJBN) a.yn[(long long)row * a.ldn + threadIdx.x] = red[threadIdx.x] * rsqrtf(fmaxf(tot, a.eps));
+    for (int e = threadIdx.x; e < nrows * kJBN; e += blockDim.x) {
+      const int r = e / kJBN, n = e - r * kJBN;
+      float tot = 0.f;
+      for (int w = 0; w < nw; ++w) tot += red[w * kT16RB + r];
+      a.yn[(long long)brow[r] * a.ldn + n] = vbuf[e] * rsqrtf(fmaxf(tot, a.eps));
+    }
   }
 }
 
@@ -896,12 +1028,27 @@ gemm_join16_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_consta
   }
   const uint32_t nbad = bad[0];   // out-of-window rows: fp32 recompute (see the header of this file)
   if (nbad != 0u) {
+    int* brow = reinterpret_cast<int*>(params);   // the epilogue constants are dead now
+    uint8_t* ring = smem;
     if (nbad <= (uint32_t)kT16BadCap) {
-      for (uint32_t i = 0; i < nbad; ++i) join16_fixup_row(a, (int)bad[4 + i], params);
+      for (uint32_t base = 0; base < nbad; base += kT16RB) {
+        const int nrows = min((int)(nbad - base), kT16RB);
+        __syncthreads();
+        if ((int)threadIdx.x < nrows) brow[threadIdx.x] = (int)bad[4 + base + threadIdx.x];
+        __syncthreads();
+        join16_fixup_batch(a, brow, nrows, ring);
+      }
     } else {
       for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
-        for (int r = 0; r < kTcBM; ++r)
-          if (mt * kTcBM + r < a.M) join16_fixup_row(a, mt * kTcBM + r, params);
+        for (int r0 = 0; r0 < kTcBM; r0 += kT16RB) {
+          const int row0 = mt * kTcBM + r0;
+          if (row0 >= a.M) break;
+          const int nrows = min(a.M - row0, kT16RB);
+          __syncthreads();
+          if ((int)threadIdx.x < nrows) brow[threadIdx.x] = row0 + threadIdx.x;
+          __syncthreads();
+          join16_fixup_batch(a, brow, nrows, ring);
+        }
     }
   }
 }

@@ -2,8 +2,9 @@
 evaluate/global_eval/evaluation_retrieval.py:29-58,129-169): k nearest reference descriptors per
 query (Euclidean, 256-D) and recall@N / top-1% against the 25 m UTM ground truth.
 
-``retrieve_topk`` runs on the GPU through the C ABI (Gram matrix with the GEMM kernel, then a
-warp-per-query top-k selection); the recall bookkeeping is host numpy like the reference."""
+``retrieve_topk`` runs on the GPU through the C ABI (Gram matrix with the GEMM kernel, a warp-per-query
+selection of k + 8 candidates, then a re-rank of those by their exactly computed distances -- the Gram form alone
+cannot order near-identical descriptors); the recall bookkeeping is host numpy like the reference."""
 import ctypes
 
 import numpy as np
@@ -26,6 +27,15 @@ def retrieve_topk(ref_desc, query_desc, k):
     rn = (ref_desc * ref_desc).sum(1).contiguous()
     idx = torch.empty((Q, k), dtype=torch.int32, device=ref_desc.device)
     val = torch.empty((Q, k), dtype=torch.float32, device=ref_desc.device)
+    if k <= 24:
+        cand = torch.empty((Q, 32), dtype=torch.int32, device=ref_desc.device)
+        cval = torch.empty((Q, 32), dtype=torch.float32, device=ref_desc.device)
+        call("dh3d_topk_l2_exact", check(gram, torch.float32, "gram"), Rp, check(qn, torch.float32, "qn"),
+             check(rn, torch.float32, "rn"), check(query_desc.contiguous(), torch.float32, "query"),
+             check(ref_desc.contiguous(), torch.float32, "ref"), Q, R, D, k, check(idx, torch.int32, "idx"),
+             check(val, torch.float32, "val"), check(cand, torch.int32, "cand"), check(cval, torch.float32, "cand_val"),
+             stream_ptr(ref_desc.device))
+        return idx, val
     call("dh3d_topk_l2", check(gram, torch.float32, "gram"), Rp, check(qn, torch.float32, "qn"),
          check(rn, torch.float32, "rn"), Q, R, k, check(idx, torch.int32, "idx"),
          check(val, torch.float32, "val"), stream_ptr(ref_desc.device))

@@ -258,6 +258,13 @@ DH3D_API int dh3d_netvlad(const float* features, const float* att, int B, int N,
  * ------------------------------------------------------------------------------------------- */
 DH3D_API int dh3d_topk_l2(const float* gram, int ldg, const float* qn, const float* rn, int Q, int R, int K,
                  int32_t* idx, float* val, void* stream);
+/* Same, with the selected neighbours re-ranked by their EXACT distances sum_d (q_d - r_d)^2 (the Gram form loses
+ * the order of near-identical descriptors to cancellation; a cKDTree computes the differences directly):
+ *   query [Q,D], ref [R,D] row-major descriptors; cand [Q,32] i32 and cand_val [Q,32] f32 are caller scratch.
+ *   The Gram pass selects min(K + 8, 32, R) candidates.  K <= 24. */
+DH3D_API int dh3d_topk_l2_exact(const float* gram, int ldg, const float* qn, const float* rn, const float* query,
+                       const float* ref, int Q, int R, int D, int K, int32_t* idx, float* val, int32_t* cand,
+                       float* cand_val, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward passes and the transposed FlexConv (training side of boundary A/B)

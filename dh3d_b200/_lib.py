@@ -92,9 +92,9 @@ _lib = None
 # kernels launched per C-ABI call (memcpy/memset nodes not counted); bench.py's gpu_launches claim
 _KERNELS_PER_CALL = {
     "dh3d_knn_bruteforce": 2, "dh3d_knn_bruteforce_pm": 2,          # pack + scan
-    "dh3d_flex_conv": 8,                                             # 4 transposes + theta_ext + moments + gemm (+memset)
-    "dh3d_flex_conv_pm": 3,                                          # theta_ext + fold_bias + the fused kernel
-    "dh3d_flex_conv_prepack": 2, "dh3d_flex_conv_pm_packed": 1,      # weights once; then the fused kernel only
+    "dh3d_flex_conv": 8,                                             # 4 transposes + 2 theta_ext + fold_bias + fused kernel
+    "dh3d_flex_conv_pm": 4,                                          # 2 theta_ext forms + fold_bias + the fused kernel
+    "dh3d_flex_conv_prepack": 3, "dh3d_flex_conv_pm_packed": 1,      # weights once; then the fused kernel only
     "dh3d_query_ball_point": 2, "dh3d_netvlad": 4, "dh3d_three_nn_ws": 3,
     "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
     "dh3d_keypoint_nms": 5,

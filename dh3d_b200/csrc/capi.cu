@@ -56,15 +56,6 @@ int rowdot_launch(const float* x, int ldx, const float* w, float bias, int act, 
 int linear_simt_launch(const float* x, int ldx, const float* w, const float* scale,
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        cudaStream_t st);
-// gemm_tc.cu
-size_t linear_prepack_bytes(int K, int N);
-int linear_prepack_launch(const float* w, int K, int N, void* packed, cudaStream_t st);
-int linear_tc_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
-                     int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
-int linear_rowdot_tc_launch(const float* x, int ldx, const void* packed, const float* scale,
-                            const float* shift, int act, const float* w2, float b2, int act2, float* y2,
-                            int M, int K, int N, cudaStream_t st);
-// gemm_tc16.cu
 size_t linear_prepack16_bytes(int K, int N);
 int linear_prepack16_launch(const float* w, int K, int N, void* packed, cudaStream_t st);
 int linear_tc16_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
@@ -139,23 +130,16 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
                    const float* gbn_scale, const float* gbn_shift, int final_l2norm, float* out,
                    void* ws, size_t ws_bytes, cudaStream_t st);
 
-// DH3D_GEMM=simt selects the exact-fp32 FFMA GEMM inside FlexConv (default: tcgen05 3xTF32).
-bool gemm_use_tc() {
-  static const bool tc = [] {
-    const char* e = getenv("DH3D_GEMM");
-    return !(e && (e[0] == 's' || e[0] == 'S'));
+// The ONE process-wide switch of this library: DH3D_EXACT_FP32=1 selects the exact-fp32 debug path -- FFMA GEMM
+// stages inside FlexConv (two-kernel form) and the FFMA NetVLAD aggregation -- instead of the tcgen05 kernels.
+// (The Python layer reads the same variable to skip dh3d_linear_prepack and call dh3d_linear.)  No buffer layout
+// depends on it: prepacked weights always carry every form a kernel may read.
+bool exact_fp32() {
+  static const bool on = [] {
+    const char* e = getenv("DH3D_EXACT_FP32");
+    return e && e[0] != '\0' && e[0] != '0';
   }();
-  return tc;
-}
-
-// Split used by the packed dense layers (dh3d_linear_prepack / _packed / _rowdot_packed; process-wide,
-// read once): default fp16 pairs on kind::f16 (gemm_tc16.cu); DH3D_GEMM_SPLIT=tf32 -> gemm_tc.cu.
-bool gemm_split_f16() {
-  static const bool f16 = [] {
-    const char* e = getenv("DH3D_GEMM_SPLIT");
-    return !(e && (e[0] == 't' || e[0] == 'T'));
-  }();
-  return f16;
+  return on;
 }
 
 // GEMM dispatch (one place to switch the dense path)
@@ -300,34 +284,24 @@ int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, con
                 int act, float* y, int ldy, int M, int K, int N, void* stream) {
   return linear_launch(x, ldx, w, scale, shift, act, y, ldy, M, K, N, S(stream));
 }
-size_t dh3d_linear_prepack_bytes(int K, int N) {
-  const size_t a = linear_prepack_bytes(K, N), b = linear_prepack16_bytes(K, N);
-  return a > b ? a : b;  // either format fits
-}
+size_t dh3d_linear_prepack_bytes(int K, int N) { return linear_prepack16_bytes(K, N); }
 int dh3d_linear_prepack(const float* w, int K, int N, void* packed, void* stream) {
-  if (gemm_split_f16()) return linear_prepack16_launch(w, K, N, packed, S(stream));
-  return linear_prepack_launch(w, K, N, packed, S(stream));
+  return linear_prepack16_launch(w, K, N, packed, S(stream));
 }
 int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                        const float* shift, int act, float* y, int ldy, int M, int K, int N,
                        void* stream) {
-  if (gemm_split_f16())
-    return linear_tc16_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
-  return linear_tc_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
+  return linear_tc16_launch(x, ldx, packed_w, scale, shift, act, y, ldy, M, K, N, S(stream));
 }
 int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, const float* scale,
                               const float* shift, int act, const float* w2, float b2, int act2,
                               float* y, int M, int K, int N, void* stream) {
-  if (gemm_split_f16())
-    return linear_rowdot_tc16_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N,
-                                     S(stream));
-  return linear_rowdot_tc_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
+  return linear_rowdot_tc16_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
 }
 int dh3d_linear_join_packed(const float* xa, int ldxa, const void* packed_wa, const float* scale_a,
                             const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_wb,
                             const float* scale_b, const float* shift_b, int act_b, float* y, int ldy,
                             float* y_normalized, int ldn, float eps, int M, int Ka, int Kb, int N, void* stream) {
-  if (!gemm_split_f16()) return DH3D_ERR_UNSUPPORTED;   // packed weights are in the 3xTF32 layout
   return linear_join_tc16_launch(xa, ldxa, packed_wa, scale_a, shift_a, act_a, xb, ldxb, packed_wb, scale_b,
                                  shift_b, act_b, y, ldy, y_normalized, ldn, eps, M, Ka, Kb, N, S(stream));
 }

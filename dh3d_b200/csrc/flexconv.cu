@@ -8,7 +8,7 @@
 // i.e. a neighbour gather-reduce into 4*Din moments (HBM/L2-bandwidth bound: each neighbour is
 // one contiguous Din-float row in point-major layout, read with 16-byte loads) followed by ONE
 // dense GEMM in which K no longer appears (flops 9*N*K*Din*Dout -> 8*N*K*Din + 8*N*Din*Dout).
-// The GEMM + feature-bias/BatchNorm/ReLU epilogue is gemm_simt.cu / gemm_tc.cu.
+// The GEMM + feature-bias/BatchNorm/ReLU epilogue of the two-kernel form is gemm_simt.cu.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -17,31 +17,10 @@ namespace dh3d {
 
 int linear_launch(const float* x, int ldx, const float* w, const float* scale, const float* shift,
                   int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
-int linear_tc_launch(const float* x, int ldx, const void* packed, const float* scale, const float* shift,
-                     int act, float* y, int ldy, int M, int K, int N, cudaStream_t st);
-size_t linear_prepack_bytes(int K, int N);
-bool gemm_use_tc();
-int flexconv_fused_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
-                          const float* scale, const float* shift, int act, float* out, int rows,
-                          int n_per_cloud, int K, int Din, int Dout, cudaStream_t st);
-bool flexconv_fused_supported(int Din, int Dout);
-int flexconv_g4_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
-                       const float* scale, const float* shift, int act, float* out, int rows, int n_per_cloud,
-                       int K, int Din, int Dout, cudaStream_t st);
-
-// Fused kernels (tensor-core path on): default = cp.async-staged neighbours (flexconv_ca.cu);
-// DH3D_FLEXCONV=g4: TMA tile::gather4 staging (flexconv_g4.cu); =regs: per-thread loads (flexconv_tc.cu);
-// =split: the two-kernel form (moments to HBM, then the GEMM).
-static int flexconv_mode() {   // 0 = ca, 1 = regs, 2 = split, 3 = g4
-  static const int m = [] {
-    const char* e = getenv("DH3D_FLEXCONV");
-    if (e && (e[0] == 's' || e[0] == 'S')) return 2;
-    if (e && (e[0] == 'r' || e[0] == 'R')) return 1;
-    if (e && (e[0] == 'g' || e[0] == 'G')) return 3;
-    return 0;
-  }();
-  return m;
-}
+bool exact_fp32();   // capi.cu: DH3D_EXACT_FP32=1 -> the two-kernel form with the FFMA GEMM
+// the fused kernel (flexconv_ca.cu) needs whole 32-channel groups and 16-byte output rows
+static bool flexconv_fused_supported(int Din, int Dout) { return Din % 32 == 0 && Dout % 4 == 0; }
+static bool flexconv_use_fused(int Din, int Dout) { return !exact_fp32() && flexconv_fused_supported(Din, Dout); }
 int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, const void* theta_packed,
                        const float* scale, const float* shift, int act, float* out, int rows, int n_per_cloud,
                        int K, int Din, int Dout, cudaStream_t st);
@@ -90,9 +69,11 @@ flexconv_moments_kernel(const float* __restrict__ feat, const float* __restrict_
 static size_t moments_bytes(int B, int N, int Din) {
   return align_up((size_t)B * N * 4 * Din * sizeof(float), 256);
 }
-static size_t theta_ext_bytes(int Din, int Dout) {
-  return linear_prepack_bytes(4 * Din, Dout);  // room for the {hi^T, lo^T} packed form
-}
+// Theta_ext in BOTH operand forms, back to back: plain [4*Din, Dout] fp32 (FFMA GEMM of the two-kernel form), then
+// {hi^T, lo^T} [Dout, 4*Din] tf32 pairs (fused tcgen05 kernel).  A prepacked buffer therefore never depends on
+// which path the process runs.
+static size_t theta_plane_bytes(int Din, int Dout) { return align_up((size_t)4 * Din * Dout * sizeof(float), 256); }
+static size_t theta_ext_bytes(int Din, int Dout) { return 3 * theta_plane_bytes(Din, Dout); }
 
 size_t flex_conv_pm_workspace_bytes(int B, int N, int K, int Din, int Dout) {
   (void)K;
@@ -150,7 +131,7 @@ size_t flex_conv_pm_total_workspace_bytes(int B, int N, int K, int Din, int Dout
 }
 
 // ---- weight-only preparation (Theta_ext in the contraction's operand form + the folded shift) ----------
-// packed = [Theta_ext (plain, or {hi^T, lo^T} for the tensor-core path) | fshift[Dout]].  Depends on the
+// packed = [Theta_ext plain | Theta_ext^T hi | Theta_ext^T lo | fshift[Dout]].  Depends on the
 // layer's weights only, so an inference caller prepares it once (dh3d_flex_conv_prepack) instead of
 // re-deriving it in every forward (two extra launches per layer, ~6 us each with their gaps).
 size_t flex_conv_prepack_bytes(int Din, int Dout) {
@@ -164,15 +145,12 @@ static int flex_conv_prepack_padded(const float* theta, const float* bias, const
   float* theta_ext = reinterpret_cast<float*>(packed);
   float* fshift = reinterpret_cast<float*>(reinterpret_cast<char*>(packed) + theta_ext_bytes(Din, Dout));
   // Theta_ext = [bias ; theta_x ; theta_y ; theta_z]  (logical dims may be smaller than the padded ones)
-  if (gemm_use_tc()) {
-    float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) +
-                                         align_up((size_t)4 * Din * Dout * sizeof(float), 256));
-    theta_ext_packed_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(
-        theta, bias, theta_ext, lo, din_logical, dout_logical, Din, Dout);
-  } else {
-    theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
-                                                                   dout_logical, Din, Dout);
-  }
+  float* hi = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) + theta_plane_bytes(Din, Dout));
+  float* lo = reinterpret_cast<float*>(reinterpret_cast<char*>(theta_ext) + 2 * theta_plane_bytes(Din, Dout));
+  theta_ext_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(theta, bias, theta_ext, din_logical,
+                                                                 dout_logical, Din, Dout);
+  theta_ext_packed_kernel<<<ceil_div(4 * Din * Dout, 256), 256, 0, st>>>(
+      theta, bias, hi, lo, din_logical, dout_logical, Din, Dout);
   fold_bias_kernel<<<ceil_div(Dout, 128), 128, 0, st>>>(feature_bias, scale, shift, fshift, Dout);
   return launch_status();
 }
@@ -193,8 +171,8 @@ static int flex_conv_run(const float* feat, const float* theta_ext, const float*
 size_t flex_conv_pm_packed_workspace_bytes(int B, int N, int K, int Din, int Dout) {
   (void)K;
   if (B <= 0 || N <= 0 || Din <= 0 || Dout <= 0) return 0;
-  // only the two-kernel form (DH3D_FLEXCONV=split / DH3D_GEMM=simt / unsupported dims) needs the moment matrix
-  if (gemm_use_tc() && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) return 256;
+  // only the two-kernel form (DH3D_EXACT_FP32 / dims the fused kernel does not cover) needs the moment matrix
+  if (flexconv_use_fused(Din, Dout)) return 256;
   return moments_bytes(B, N, Din);
 }
 
@@ -245,35 +223,21 @@ static int flex_conv_run(const float* feat, const float* theta_ext_c, const floa
                          const float* xyz, float* out, int B, int N, int K, int Din, int Dout,
                          const float* scale, int act, float* A, cudaStream_t st) {
   float* theta_ext = const_cast<float*>(theta_ext_c);   // the launchers take non-const operand pointers
-  const bool tc = gemm_use_tc();
   const long long rows = (long long)B * N;
   if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
-  if (tc && flexconv_mode() != 2 && flexconv_fused_supported(Din, Dout)) {
-    // measured (B200, r1o, 32 x 8192 points, K = 8): cp.async staging with the unrolled K == 8 schedule
-    // 0.171 ms at 64->64 (0.207 generic loop) and 0.112 ms at 32->64 (per-thread gather: 0.121 ms)
-    static const int ca_min_din = getenv("DH3D_FLEXCONV_CA_MIN_DIN") ? atoi(getenv("DH3D_FLEXCONV_CA_MIN_DIN")) : 32;
-    // Din = 32 takes the cp.async kernel through its K == 8 schedule only (the shape every test and the forward
-    // exercise); other K at Din = 32 stay on the per-thread-gather kernel as before
-    if (flexconv_mode() == 0 && (Din >= 64 || (Din >= ca_min_din && K == 8)))
-      return flexconv_ca_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
-                                Dout, st);
-    if (flexconv_mode() == 3)
-      return flexconv_g4_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
-                                Dout, st);
-    return flexconv_fused_launch(feat, xyz, nbr, theta_ext, scale, eff_shift, act, out, (int)rows, N, K, Din,
-                                 Dout, st);
+  if (flexconv_use_fused(Din, Dout)) {
+    // cp.async-staged gather + tcgen05 contraction in one kernel; staging A/B (TMA tile::gather4 1.46x slower,
+    // per-thread LDG 1.31x slower at 64->64 x 262144 points): profiles/flexconv_staging_ab_r2f.json
+    const float* hi = reinterpret_cast<const float*>(reinterpret_cast<const char*>(theta_ext) +
+                                                     theta_plane_bytes(Din, Dout));
+    return flexconv_ca_launch(feat, xyz, nbr, hi, scale, eff_shift, act, out, (int)rows, N, K, Din, Dout, st);
   }
   long long blocks = (rows * (Din / 4) + 255) / 256;
   if (blocks > (long long)kNumSMs * 16) blocks = (long long)kNumSMs * 16;
   flexconv_moments_kernel<<<(int)blocks, 256, 0, st>>>(feat, xyz, nbr, A, rows, N, K, Din);
   int rc = launch_status();
   if (rc != DH3D_OK) return rc;
-  if (rows > 0x7fffffffLL) return DH3D_ERR_UNSUPPORTED;
-  if (tc)
-    return linear_tc_launch(A, 4 * Din, theta_ext, scale, eff_shift, act, out, Dout, (int)rows, 4 * Din,
-                            Dout, st);
-  return linear_launch(A, 4 * Din, theta_ext, scale, eff_shift, act, out, Dout, (int)rows, 4 * Din,
-                       Dout, st);
+  return linear_launch(A, 4 * Din, theta_ext, scale, eff_shift, act, out, Dout, (int)rows, 4 * Din, Dout, st);
 }
 
 int flex_conv_pm(const float* feat, const float* theta, const float* bias, const int32_t* nbr,

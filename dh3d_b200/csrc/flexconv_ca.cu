@@ -6,11 +6,12 @@
 //   out[n,:] = act( (A[n,:] @ Theta_ext) * scale + shift ),
 //   A[n, p'*Din + c] = sum_k (1,dx,dy,dz)[p'] * f[nbr(n,k), c],   Theta_ext = [bias; theta_x; theta_y; theta_z]
 //
-// The gather is latency-bound: what matters is how many neighbour bytes are in flight per SM.
-//   flexconv_tc.cu   per-thread LDG into registers: ~20-30 KB in flight (8 gather warps x registers); ncu r1f:
-//                    long-scoreboard stalls, 30 % issue, 19 % L2.
-//   flexconv_g4.cu   TMA tile::gather4: no registers, but measured only one 128-byte row per ~17 cycles per
-//                    SM (2.1 TB/s aggregate) -- slower than the loads it replaces.
+// The gather is latency-bound: what matters is how many neighbour bytes are in flight per SM.  Three stagings were
+// built and measured on B200 (profiles/flexconv_staging_ab_r2f.json, ncu, 64->64 x 262144 points / 128->128 x 65536):
+//   per-thread LDG into registers   215 / 135 us: ~20-30 KB in flight (8 gather warps x registers), 22 % warps active
+//   TMA tile::gather4 (4 rows/TMA)  240 / 127 us: no registers held, but 2.5x the instructions for the coordinate /
+//                                   descriptor bookkeeping and a higher latency per stalled issue
+//   cp.async ring (this file)       164 /  85 us -- kept; the other two kernels were deleted after that capture.
 //   here             every consumer thread (point x 8 channels) copies exactly the 32 bytes it will read itself
 //                    with two 16-byte cp.async, G-1 items (= neighbour slots) ahead of the one it is reducing:
 //                    512 threads x (G-1) x 32 B in flight, a pure per-thread software pipeline
@@ -523,9 +524,7 @@ int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, 
   const float* thi = reinterpret_cast<const float*>(theta_packed);
   const float* tlo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(theta_packed) +
                                                     align_up((size_t)4 * Din * Dout * sizeof(float), 256));
-  // DH3D_FLEXCONV_K8=0 sends K == 8 through the generic consumer loop (A/B comparison)
-  static const bool k8_off = getenv("DH3D_FLEXCONV_K8") && getenv("DH3D_FLEXCONV_K8")[0] == '0';
-  if (K == 8 && !k8_off && ((uintptr_t)nbr & 7) == 0) {
+  if (K == 8 && ((uintptr_t)nbr & 7) == 0) {
     if (Dout <= 64) return launch_ca<64, true>(a, thi, tlo, out, st);
     return launch_ca<128, true>(a, thi, tlo, out, st);
   }

@@ -1,10 +1,10 @@
 // Farthest point sampling (reference: tf_ops/sampling/tf_sampling_g.cu:105-170, <<<32,512>>>).
 //
 // The reference runs at most 32 CTAs, keeps the running min-distance array `temp` in GLOBAL
-// memory and pays 2 x 9 __syncthreads per round for a shared-memory tree argmax.  Here one
-// 1024-thread CTA owns one cloud (all B clouds run concurrently), the points and their running
-// min-distance live in REGISTERS (8 points/thread at n = 8192), the argmax is one REDUX.MAX +
-// ballot per warp and one barrier per round (double-buffered per-warp slots).
+// memory and pays 2 x 9 __syncthreads per round for a shared-memory tree argmax.  Here 1024 threads
+// own one cloud (all B clouds run concurrently; a 4-CTA cluster of 256 threads each, see below), the
+// points and their running min-distance live in REGISTERS (8 points/thread at n = 8192) and the argmax
+// is one REDUX.MAX + ballot per warp.
 //
 // Bit-exact parity with the reference's selection order.  The reference picks, among the points
 // with maximal d2, the one with the smallest (k mod 512, k): thread tid scans k=tid,tid+512,..
@@ -40,60 +40,8 @@ __device__ __forceinline__ int fps_block_argmax(float best, int besti, int* s_va
   return __shfl_sync(0xffffffffu, i, __ffs(m2) - 1);
 }
 
-// Register-resident variant: n <= 1024 * PPT, xyz cached in shared memory for the centre lookup.
-template <int PPT>
-__global__ void __launch_bounds__(kFpsThreads, 1)
-fps_reg_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __restrict__ idxs) {
-  extern __shared__ __align__(16) float s_xyz[];  // n*3 floats
-  __shared__ int s_val[2][kFpsWarps];
-  __shared__ int s_idx[2][kFpsWarps];
-
-  const int b = blockIdx.x;
-  const float* ds = dataset + (long long)b * n * 3;
-  int32_t* out = idxs + (long long)b * m;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  for (int j = tid; j < n * 3; j += kFpsThreads) s_xyz[j] = ds[j];
-  __syncthreads();
-
-  const int V = (n + 511) >> 9;
-  const unsigned magic = 0xffffffffu / (unsigned)V + 1u;  // tk / V == umulhi(tk, magic), tk < 2^16
-  float px[PPT], py[PPT], pz[PPT], td[PPT];
-#pragma unroll
-  for (int i = 0; i < PPT; ++i) {
-    const int tk = tid * PPT + i;
-    const int k = (tk % V) * 512 + tk / V;
-    const bool valid = (tk < 512 * V) && (k < n);
-    px[i] = valid ? __ldg(ds + k * 3 + 0) : 0.f;
-    py[i] = valid ? __ldg(ds + k * 3 + 1) : 0.f;
-    pz[i] = valid ? __ldg(ds + k * 3 + 2) : 0.f;
-    td[i] = valid ? 1e38f : -1.f;  // -1 pins d2 = min(d,-1) = -1, which never beats best = -1
-  }
-
-  int old = 0;
-  if (tid == 0) out[0] = 0;
-  for (int j = 1; j < m; ++j) {
-    const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
-    float best = -1.f;
-    int bslot = 0;
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-      const float dx = px[i] - x1, dy = py[i] - y1, dz = pz[i] - z1;
-      const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-      const float d2 = fminf(d, td[i]);
-      td[i] = d2;
-      if (d2 > best) { best = d2; bslot = i; }
-    }
-    const unsigned tk = (unsigned)fps_block_argmax(best, tid * PPT + bslot, s_val[j & 1],
-                                                   s_idx[j & 1], lane, warp);
-    const unsigned q = (V == 1) ? tk : __umulhi(tk, magic);
-    old = (int)((tk - q * (unsigned)V) * 512u + q);
-    if (tid == 0) out[j] = old;
-  }
-}
-
-// ---- 4-CTA cluster variant (default for n <= 8192) ----------------------------------------------
-// The single-CTA kernel above is ISSUE-bound, not latency-bound: 32 warps x ~105 instructions per
+// ---- 4-CTA cluster kernel (n <= 8192) ---------------------------------------------------------
+// A single 1024-thread CTA per cloud (the first version of this file, 0.71 ms) is ISSUE-bound, not latency-bound: 32 warps x ~105 instructions per
 // round on one SM's four schedulers = ~840 of the ~1375 cycles a round takes (ncu r1h), while 116
 // of the 148 SMs idle at B = 32.  Here a cluster of 4 CTAs x 256 threads owns one cloud: the same
 // 32 warps, two per scheduler over four SMs.  There is NO barrier inside the round loop: lane r of
@@ -288,19 +236,10 @@ fps_smem_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __rest
 }
 
 template <int PPT>
-static int fps_launch_reg(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
-  size_t smem = (size_t)n * 3 * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(fps_reg_kernel<PPT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  fps_reg_kernel<PPT><<<b, kFpsThreads, smem, st>>>(n, m, inp, out);
-  return launch_status();
-}
-
-template <int PPT>
 static int fps_launch_cluster(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
-  static const bool xyz_global = getenv("DH3D_FPS_XYZ") && getenv("DH3D_FPS_XYZ")[0] == 'g';
-  const int xyz_in_smem = xyz_global ? 0 : 1;
+  // the cloud's coordinates live in each CTA's shared memory (reading them through L1 instead, so that other
+  // CTAs could share the SM, measured slower: 0.59 vs 0.45 ms in the step, r1v)
+  const int xyz_in_smem = 1;
   size_t smem = xyz_in_smem ? (size_t)n * 3 * sizeof(float) : 0;
   cudaError_t e = cudaFuncSetAttribute(fps_cluster_kernel<PPT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -322,15 +261,6 @@ static int fps_launch_cluster(int b, int n, int m, const float* inp, int32_t* ou
   return launch_status();
 }
 
-// DH3D_FPS=cta selects the single-CTA kernel (read once).
-static bool fps_use_cluster() {
-  static const bool v = [] {
-    const char* e = getenv("DH3D_FPS");
-    return !(e && (e[0] == 'c' || e[0] == 'C') && (e[1] == 't' || e[1] == 'T'));
-  }();
-  return v;
-}
-
 int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t st) {
   if (!inp || !out) return DH3D_ERR_NULL;
   if (b <= 0 || n <= 0 || m < 0) return DH3D_ERR_DIM;
@@ -338,16 +268,13 @@ int fps_launch(int b, int n, int m, const float* inp, int32_t* out, cudaStream_t
   if (n > 65536) return DH3D_ERR_UNSUPPORTED;
   const int total = 512 * ((n + 511) / 512);
   const int ppt = ceil_div(total, kFpsThreads);
-  if (ppt <= 8 && fps_use_cluster()) {  // 4 x 256 threads per cloud: same points-per-thread split
+  if (ppt <= 8) {  // n <= 8192: a 4-CTA cluster of 256 threads per cloud
     if (ppt <= 1) return fps_launch_cluster<1>(b, n, m, inp, out, st);
     if (ppt <= 2) return fps_launch_cluster<2>(b, n, m, inp, out, st);
     if (ppt <= 4) return fps_launch_cluster<4>(b, n, m, inp, out, st);
     return fps_launch_cluster<8>(b, n, m, inp, out, st);
   }
-  if (ppt <= 1) return fps_launch_reg<1>(b, n, m, inp, out, st);
-  if (ppt <= 2) return fps_launch_reg<2>(b, n, m, inp, out, st);
-  if (ppt <= 4) return fps_launch_reg<4>(b, n, m, inp, out, st);
-  if (ppt <= 8) return fps_launch_reg<8>(b, n, m, inp, out, st);
+  // n > 8192 (outside DH3D's shapes): one CTA per cloud, min-distances in shared memory
   size_t smem = (size_t)total * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(fps_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);

@@ -443,8 +443,7 @@ int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points,
 #define DH3D_TI(V, FD)                                                                          \
   three_interp_kernel<V, FD><<<ew_blocks(rows * (c / V), 256), 256, 0, st>>>(points, idx, wsrc, out, \
                                                                             rows, n, m, c, ldo)
-  static const bool elementwise = getenv("DH3D_INTERP") && !strcmp(getenv("DH3D_INTERP"), "elem");
-  if (vec && !elementwise) {
+  if (vec) {   // warp-per-row kernel; the element-per-thread kernel below only serves c % 4 != 0 / unaligned rows
     const int blocks = ew_blocks(((rows + 7) / 8) * 32, 256);
     if (from_dist)
       three_interp_warp_kernel<true><<<blocks, 256, 0, st>>>(points, idx, wsrc, out, rows, n, m, c, ldo);
@@ -452,8 +451,7 @@ int three_interpolate_ld_launch(int b, int m, int c, int n, const float* points,
       three_interp_warp_kernel<false><<<blocks, 256, 0, st>>>(points, idx, wsrc, out, rows, n, m, c, ldo);
     return launch_status();
   }
-  if (vec) { if (from_dist) DH3D_TI(4, true); else DH3D_TI(4, false); }
-  else { if (from_dist) DH3D_TI(1, true); else DH3D_TI(1, false); }
+  if (from_dist) DH3D_TI(1, true); else DH3D_TI(1, false);
 #undef DH3D_TI
   return launch_status();
 }

@@ -2,7 +2,7 @@
 //   X [M,K] row-major (ldx), W [K,N] row-major, Y [M,N] row-major (ldy).
 // Exact-fp32 (FFMA) path used for (1) the FlexConv contraction  A[N, 4*Din] @ Theta_ext[4*Din, Dout]
 // and (2) the dense 1x1 stacks, whenever bit-faithful fp32 accumulation is wanted; the
-// tensor-core (tcgen05, 3xTF32 split) path lives in gemm_tc.cu.
+// tensor-core (tcgen05, fp16-pair split) path lives in gemm_tc16.cu.
 // 128 x BN x 16 CTA tile, 256 threads, 8 x (BN/16) register tile per thread, register-staged
 // double buffering of the next K slab.
 #include "common.cuh"

@@ -2,7 +2,7 @@
 //   optionally fused with a following 1-column layer:  y[m] = act2( sum_n Y[m,n] * w2[n] + b2 )
 //
 // tcgen05.mma kind::f16 runs at twice the kind::tf32 rate, and a 2-term fp16 split carries 22 mantissa
-// bits just like the tf32 split of gemm_tc.cu, so the same 3 MMAs per product cost half the time:
+// bits just like a 3xTF32 split, so the same 3 MMAs per product cost half the time:
 //     x' = x * 2^4          = xh + xl      (xh = fp16(x'), xl = fp16(x' - xh))
 //     w' = w * sw[n]        = wh + wl      (sw[n] = power of two putting max_k |w[k,n]| in [2^13, 2^14))
 //     x'*w' ~= xl*wh + xh*wl + xh*wh       (dropped xl*wl ~ 2^-22 relative), result * 2^-4 / sw[n]
@@ -18,7 +18,7 @@
 // IMNMX per element on the first N pass and a never-taken branch; out-of-distribution clouds cost
 // ~3 us per affected row instead of poisoning the descriptors (round-1 ADVICE / VERDICT item 5).
 //
-// Same persistent warp-specialised structure as gemm_tc.cu (320 threads, one CTA per SM, 2-CTA
+// Persistent warp-specialised structure (320 threads, one CTA per SM, 2-CTA
 // clusters multicasting the W tiles), with
 //   * K slabs of 32: raw X tile [128 x 32] fp32 (TMA, 128B swizzle) -> warps 2-5 write xh / xl as
 //     [128 x 32] fp16 tiles in the 64B-swizzled K-major layout (conflict-free 16-byte loads/stores);
@@ -145,7 +145,7 @@ __device__ __forceinline__ void t16_stage_rows(float* xs, const float* x, int ld
 // the whole batch (lane l owns k = 8l .. 8l+7, +256 per round; 16-byte loads), reduces with shuffles and applies
 // the epilogue.  y[row, n] = act((x[row, :] @ W[:, n]) * scale[n] + shift[n]) with W = (wh + wl) * colscale * 2^4.
 template <bool ROWDOT>
-__device__ __noinline__ void t16_fixup_batch(const T16Epilogue& ep, const int* brow, int nrows, int K, int N, float* xs,
+__device__ __forceinline__ void t16_fixup_batch(const T16Epilogue& ep, const int* brow, int nrows, int K, int N, float* xs,
                                              float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   __syncthreads();
@@ -202,7 +202,7 @@ __device__ __forceinline__ float t16_row_dot(const float* __restrict__ xr, const
 
 // one row at a time (K > kT16FixMaxK): same arithmetic, activations read from global memory
 template <bool ROWDOT>
-__device__ __noinline__ void t16_fixup_row(const T16Epilogue& ep, int row, int K, int N, float* red) {
+__device__ __forceinline__ void t16_fixup_row(const T16Epilogue& ep, int row, int K, int N, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float* xr = ep.x + (long long)row * ep.ldx;
   float part = 0.f;
@@ -622,14 +622,6 @@ static int make_map_f16(CUtensorMap* m, const __half* base, long long rows, long
   return r == CUDA_SUCCESS ? DH3D_OK : DH3D_ERR_UNSUPPORTED;
 }
 
-static bool t16_use_multicast() {
-  static const bool on = [] {
-    const char* e = getenv("DH3D_GEMM_MULTICAST");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
-
 template <int BN, bool ROWDOT, int MC>
 static int launch_t16_mc(const float* x, int ldx, const __half* wh, const __half* wl, const T16Epilogue& ep,
                          float* y, int ldy, int M, int K, int N, cudaStream_t st) {
@@ -670,7 +662,7 @@ template <int BN, bool ROWDOT>
 static int launch_t16(const float* x, int ldx, const __half* wh, const __half* wl, const T16Epilogue& ep,
                       float* y, int ldy, int M, int K, int N, cudaStream_t st) {
   // pairs of CTAs share each W tile when there are enough M tiles to pair up and W is re-streamed
-  if (BN >= 64 && t16_use_multicast() && ceil_div(M, kTcBM) >= 2 * 16)
+  if (BN >= 64 && ceil_div(M, kTcBM) >= 2 * 16)
     return launch_t16_mc<BN, ROWDOT, 2>(x, ldx, wh, wl, ep, y, ldy, M, K, N, st);
   return launch_t16_mc<BN, ROWDOT, 1>(x, ldx, wh, wl, ep, y, ldy, M, K, N, st);
 }
@@ -759,7 +751,7 @@ struct JoinArgs {
 
 // fp32 recompute of up to RB rows of the join by the whole CTA, one warp per output column (see t16_fixup_batch).
 // ring: [RB*Ka | RB*Kb | RB*128 floats (the rows' sums, for the norm pass) | nw*RB floats]
-__device__ __noinline__ void join16_fixup_batch(const JoinArgs& a, const int* brow, int nrows, uint8_t* ring) {
+__device__ __forceinline__ void join16_fixup_batch(const JoinArgs& a, const int* brow, int nrows, uint8_t* ring) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float* xsa = reinterpret_cast<float*>(ring);
   float* xsb = xsa + kT16RB * a.Ka;

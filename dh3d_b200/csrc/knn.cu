@@ -22,17 +22,12 @@
 // current K-th key passes); the exact compare happens only on that rare path.  The box lower bound
 // uses the same mul/fma sequence as the distance, so by monotonicity of each rounded operation it never
 // exceeds the computed d^2 of any point inside the box: skipping is exact.
-// DH3D_KNN=tiled selects the exhaustive shared-memory-tiled scan of knn_tiled.cu instead.
 #include <limits.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace dh3d {
-
-size_t knn_tiled_workspace_bytes(int B, int N);
-int knn_tiled_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
-                     float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 constexpr int kKnnChunk = 32;       // candidates per bounding box (one per lane of the box-building warp)
 constexpr int kKnnSuper = 16;       // chunks per second-level box (512 points)
@@ -75,20 +70,10 @@ static inline size_t knn_box_f4(int Np) {
   return 2 * (size_t)(Np / kKnnChunk) + 2 * (size_t)ceil_div(Np / kKnnChunk, kKnnSuper);
 }
 
-static bool knn_use_tiled() {
-  static const bool t = [] {
-    const char* e = getenv("DH3D_KNN");
-    return e && (e[0] == 't' || e[0] == 'T');
-  }();
-  return t;
-}
-
 size_t knn_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0) return 0;
   const size_t np = knn_padded(N);
-  const size_t pruned = (size_t)B * (np + knn_box_f4((int)np)) * sizeof(float4);
-  const size_t tiled = knn_tiled_workspace_bytes(B, N);
-  return pruned > tiled ? pruned : tiled;
+  return (size_t)B * (np + knn_box_f4((int)np)) * sizeof(float4);
 }
 
 __device__ __forceinline__ long long knn_box_f4_dev(int Np) {
@@ -654,19 +639,10 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   }
 }
 
-static int knn_flush_min() {
-  static const int v = [] {
-    const char* e = getenv("DH3D_KNN_FLUSH");
-    const int x = e ? atoi(e) : 1;
-    return x < 1 ? 1 : x;
-  }();
-  return v;
-}
+static int knn_flush_min() { return 1; }   // flush the candidate buffer at the end of every chunk
 
 int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
                float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (knn_use_tiled())
-    return knn_tiled_launch(pos, B, N, K, sb, sp, sd, ids, dists, workspace, workspace_bytes, st);
   if (!pos || !ids || !dists) return DH3D_ERR_NULL;
   if (B <= 0 || N <= 0 || K <= 0) return DH3D_ERR_DIM;
   if (K > 64 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;

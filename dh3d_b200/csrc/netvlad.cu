@@ -277,18 +277,13 @@ static size_t nv_part_h_bytes(int B) {
   return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
 }
 
-// netvlad_tc.cu: the aggregation on the tensor cores (default); DH3D_NETVLAD=simt keeps the FFMA kernel above
+// netvlad_tc.cu: the aggregation on the tensor cores (default); DH3D_EXACT_FP32=1 selects the FFMA kernel above
 size_t netvlad_tc_workspace_bytes();
 int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, int N, const float* cw,
                                 const float* bn_scale, const float* bn_shift, float* part_v, float* part_s,
                                 int* P_out, void* ws, cudaStream_t st);
-static bool netvlad_use_tc() {
-  static const bool tc = [] {
-    const char* e = getenv("DH3D_NETVLAD");
-    return !(e && (e[0] == 's' || e[0] == 'S'));
-  }();
-  return tc;
-}
+bool exact_fp32();   // capi.cu
+static bool netvlad_use_tc() { return !exact_fp32(); }
 
 size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
   (void)N;

@@ -38,21 +38,6 @@ constexpr uint32_t kHSlab = kNT * 128;          // 8 KB: [64 rows x 64 fp16]
 constexpr float kXScale = 4096.f;               // 2^12
 constexpr float kAScale = 16384.f;              // 2^14
 
-struct NvSmem {
-  static constexpr uint32_t raw = 0;                          // 8 slabs x 8 KB
-  static constexpr uint32_t xh = raw + 8 * kRawSlab;          // 4 slabs x 8 KB
-  static constexpr uint32_t xl = xh + 4 * kHSlab;
-  static constexpr uint32_t wh = xl + 4 * kHSlab;             // 4 slabs x 8 KB  (W^T hi, K-major)
-  static constexpr uint32_t wl = wh + 4 * kHSlab;
-  static constexpr uint32_t ah = wl + 4 * kHSlab;             // [64 k rows x 64 points] fp16
-  static constexpr uint32_t al = ah + kHSlab;
-  static constexpr uint32_t ss = al + kHSlab;                 // [2 parity][2 halves][64] partial row sums of squares
-  static constexpr uint32_t prm = ss + 2 * 2 * 64 * 4;        // [2][64]: logit scale, shift
-  static constexpr uint32_t ssum = prm + 2 * 64 * 4;          // [4 warps][64] S partials at flush
-  static constexpr uint32_t bars = ssum + 4 * 64 * 4;
-  static constexpr uint32_t total = bars + 256;
-};
-
 struct NvArgs {
   const float* att;        // [B, N]
   const float* colscale;   // [64] from linear_prepack16: 2^-4 / sw[k]
@@ -102,283 +87,11 @@ __device__ __forceinline__ void nv_split8(const float4& a, const float4& b, floa
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(kNThreads, 1)
-netvlad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWh,
-                  const __grid_constant__ CUtensorMap tmWl, const NvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NvSmem::bars);
-  uint64_t* raw_full = bars;         // [8] count 1 + tx
-  uint64_t* raw_empty = bars + 8;    // [8] count 64 (the split threads of that half row)
-  uint64_t* x_full = bars + 16;      // count 128: xh/xl written
-  uint64_t* x_free = bars + 17;      // count 1: second product done (xh/xl/a reusable)
-  uint64_t* l_full = bars + 18;      // count 1: logits in TMEM
-  uint64_t* a_full = bars + 19;      // count 128: assignment tile written
-  uint64_t* v_full = bars + 20;      // count 1: sub-slab accumulated
-  uint64_t* v_empty = bars + 21;     // count 128: V read back
-  uint64_t* w_full = bars + 22;      // count 1 + tx
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
-  float* s_ss = reinterpret_cast<float*>(smem + NvSmem::ss);
-  float* s_prm = reinterpret_cast<float*>(smem + NvSmem::prm);
-  float* s_sum = reinterpret_cast<float*>(smem + NvSmem::ssum);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, c = blockIdx.x;
-  const int tiles_cloud = (a.N + kNT - 1) / kNT;
-  const int t_begin = c * a.tiles_per_cta;
-  const int t_end = min(tiles_cloud, t_begin + a.tiles_per_cta);
-  const int ntiles = max(0, t_end - t_begin);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 8; ++s) {
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], 64);
-    }
-    mbar_init(x_full, 128);
-    mbar_init(x_free, 1);
-    mbar_init(l_full, 1);
-    mbar_init(a_full, 128);
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 128);
-    mbar_init(w_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(256)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (threadIdx.x >= 192 && threadIdx.x < 256) {  // epilogue constants: logit = raw * scale + shift
-    const int k = threadIdx.x - 192;
-    s_prm[k] = __ldg(a.colscale + k) * (16.f / kXScale) * __ldg(a.bn_scale + k);
-    s_prm[64 + k] = __ldg(a.bn_shift + k);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_logits = tmem_base;        // 64 columns, M = 64 layout (16 lanes per warp quadrant)
-  const uint32_t tm_v = tmem_base + 64;        // 2 x 64 columns, M = 128
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, 8 * kHSlab);
-      for (int s = 0; s < 4; ++s) {
-        tma_load_2d(smem + NvSmem::wh + s * kHSlab, &tmWh, s * 64, 0, w_full);
-        tma_load_2d(smem + NvSmem::wl + s * kHSlab, &tmWl, s * 64, 0, w_full);
-      }
-      for (int i = 0; i < ntiles; ++i) {
-        const int row0 = b * a.N + (t_begin + i) * kNT;
-        for (int s = 0; s < 8; ++s) {
-          mbar_wait(&raw_empty[s], (i & 1) ^ 1);
-          mbar_arrive_expect_tx(&raw_full[s], kRawSlab);
-          tma_load_2d(smem + NvSmem::raw + s * kRawSlab, &tmX, s * 32, row0, &raw_full[s]);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // D=f32, A=B=f16: first product M=64,N=64, both K-major; second M=128,N=64, A MN-major
-      const uint32_t idesc1 = (1u << 4) | ((uint32_t)(kNK >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 15) | ((uint32_t)(kNK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t xh = smem_u32(smem + NvSmem::xh), xl = smem_u32(smem + NvSmem::xl);
-      const uint32_t wh = smem_u32(smem + NvSmem::wh), wl = smem_u32(smem + NvSmem::wl);
-      const uint32_t ah = smem_u32(smem + NvSmem::ah), al = smem_u32(smem + NvSmem::al);
-      mbar_wait(w_full, 0);
-      for (int i = 0; i < ntiles; ++i) {
-        const int f = i / kNFlush, fi = i - f * kNFlush;
-        // ---- logits = Xn . W
-        mbar_wait(x_full, i & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t off = s * kHSlab + k * 32;
-            const uint64_t a_h = umma_desc_sw128(xh + off), a_l = umma_desc_sw128(xl + off);
-            const uint64_t b_h = umma_desc_sw128(wh + off), b_l = umma_desc_sw128(wl + off);
-            nv_umma_f16(tm_logits, a_l, b_h, idesc1, (s | k) != 0 ? 1u : 0u);
-            nv_umma_f16(tm_logits, a_h, b_l, idesc1, 1u);
-            nv_umma_f16(tm_logits, a_h, b_h, idesc1, 1u);
-          }
-        umma_commit(l_full);
-        // ---- V += Xn^T . A
-        mbar_wait(a_full, i & 1);
-        if (fi == 0 && f > 0) mbar_wait(v_empty, (f - 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t aoff = 2 * h * kHSlab + k * 2048;   // 16 point rows per K step
-            const uint64_t a_h = umma_desc_mn_sw128(xh + aoff, kHSlab), a_l = umma_desc_mn_sw128(xl + aoff, kHSlab);
-            const uint64_t b_h = umma_desc_sw128(ah + k * 32), b_l = umma_desc_sw128(al + k * 32);
-            const uint32_t acc = (fi | k) != 0 ? 1u : 0u;
-            nv_umma_f16(tm_v + h * 64, a_l, b_h, idesc2, acc);
-            nv_umma_f16(tm_v + h * 64, a_h, b_l, idesc2, 1u);
-            nv_umma_f16(tm_v + h * 64, a_h, b_h, idesc2, 1u);
-          }
-        umma_commit(x_free);
-        if (fi == kNFlush - 1 || i == ntiles - 1) umma_commit(v_full);
-      }
-    }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ norms + fp16 split (128 threads)
-    const int t = threadIdx.x - 64;
-    const int r = t & 63, half = t >> 6;   // row of the tile; slabs 4*half .. 4*half+3 (128 features)
-    const uint8_t* raw = smem + NvSmem::raw;
-    for (int i = 0; i < ntiles; ++i) {
-      // pass 1: sum of squares of this thread's half row
-      float ssq = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int s = 4 * half + j;
-        mbar_wait(&raw_full[s], i & 1);
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const float4 v = *reinterpret_cast<const float4*>(raw + s * kRawSlab + r * 128 + ((cc ^ (r & 7)) << 4));
-          ssq = fmaf(v.x, v.x, ssq); ssq = fmaf(v.y, v.y, ssq); ssq = fmaf(v.z, v.z, ssq); ssq = fmaf(v.w, v.w, ssq);
-        }
-      }
-      float* ssb = s_ss + (i & 1) * 128;
-      ssb[half * 64 + r] = ssq;
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      const float inv = rsqrtf(fmaxf(ssb[r] + ssb[64 + r], 1e-12f)) * kXScale;  // tf.nn.l2_normalize epsilon
-      // pass 2: xn * 2^12 -> fp16 hi/lo, 8 features per 16-byte chunk; xh/xl of the previous tile must be consumed
-      mbar_wait(x_free, (i & 1) ^ 1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int s = 4 * half + j;            // raw slab: features 32s .. 32s+31
-        uint8_t* dh = smem + NvSmem::xh + (s >> 1) * kHSlab + r * 128;
-        uint8_t* dl = smem + NvSmem::xl + (s >> 1) * kHSlab + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v0 = *reinterpret_cast<const float4*>(raw + s * kRawSlab + r * 128 + (((2 * q) ^ (r & 7)) << 4));
-          const float4 v1 =
-              *reinterpret_cast<const float4*>(raw + s * kRawSlab + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
-          uint4 hi, lo;
-          nv_split8(v0, v1, inv, hi, lo);
-          const uint32_t off = ((((s & 1) << 2) + q) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(dh + off) = hi;
-          *reinterpret_cast<uint4*>(dl + off) = lo;
-        }
-        mbar_arrive(&raw_empty[s]);
-      }
-      fence_proxy_async();
-      mbar_arrive(x_full);
-    }
-  } else if (warp < 10) {
-    // ------------------------------------------------------------------ softmax + flush (128 threads)
-    const int q = warp & 3;                 // TMEM lane quadrant
-    const bool owner = lane < 16;           // M = 64 accumulator: rows 16q .. 16q+15 sit in lanes 0..15
-    const int row = 16 * q + (lane & 15);
-    float mys[4] = {0.f, 0.f, 0.f, 0.f};    // S[k] partials of this warp, k = 16j + (lane & 15)
-    for (int f = 0; f < a.subslabs; ++f) {
-      const int i0 = f * kNFlush, i1 = min(ntiles, i0 + kNFlush);
-      for (int i = i0; i < i1; ++i) {
-        mbar_wait(l_full, i & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tm_logits + ((uint32_t)(q * 32) << 16);
-        DH3D_TMEM_LD_32X32(r0, taddr);
-        DH3D_TMEM_LD_32X32(r1, taddr + 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float p[64];
-        float mx = -CUDART_INF_F;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          p[k] = fmaf(__uint_as_float(r0[k]), s_prm[k], s_prm[64 + k]);
-          p[32 + k] = fmaf(__uint_as_float(r1[k]), s_prm[32 + k], s_prm[96 + k]);
-        }
-#pragma unroll
-        for (int k = 0; k < 64; ++k) mx = fmaxf(mx, p[k]);
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 64; ++k) { p[k] = __expf(p[k] - mx); sum += p[k]; }
-        const int n = (t_begin + i) * kNT + row;
-        float scale = 0.f;
-        if (owner && n < a.N) scale = __ldg(a.att + (long long)b * a.N + n) / sum;
-        // assignment tile: B operand [64 k rows x 64 points], K-major, 128B swizzle: element (k, row)
-        uint8_t* pah = smem + NvSmem::ah;
-        uint8_t* pal = smem + NvSmem::al;
-        const uint32_t col = ((row >> 3) << 4), sub = (row & 7) * 2;   // 16-byte chunk (8 points), byte inside it
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-          const float av = p[k] * scale;          // in [0, 1]
-          // S[k] += sum over the 16 rows of this warp
-          float sv = owner ? av : 0.f;
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-          if ((k & 15) == (lane & 15)) mys[k >> 4] += sv;
-          if (owner) {
-            const float as = av * kAScale;
-            const __half h = __float2half_rn(as);
-            const __half l = __float2half_rn(as - __half2float(h));
-            const uint32_t off = k * 128 + ((((col >> 4) ^ (k & 7))) << 4) + sub;
-            *reinterpret_cast<__half*>(pah + off) = h;
-            *reinterpret_cast<__half*>(pal + off) = l;
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        fence_proxy_async();
-        mbar_arrive(a_full);
-      }
-      // ---- flush the sub-slab: V (TMEM, all 128 lanes) -> part_v, S -> part_s
-      const int pidx = c * a.subslabs + f;
-      float* pv = a.part_v + ((long long)(b * a.P + pidx) * kND) * kNK;
-      if (i1 > i0) {
-        mbar_wait(v_full, f & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int d = h * 128 + q * 32 + lane;
-#pragma unroll 1
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint32_t rv[32];
-            DH3D_TMEM_LD_32X32(rv, tm_v + h * 64 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float4* dst = reinterpret_cast<float4*>(pv + (long long)d * kNK + c0);
-            const float sc = 1.f / (kXScale * kAScale);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(__uint_as_float(rv[4 * j]) * sc, __uint_as_float(rv[4 * j + 1]) * sc,
-                                   __uint_as_float(rv[4 * j + 2]) * sc, __uint_as_float(rv[4 * j + 3]) * sc);
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(v_empty);
-      } else {
-        for (int e = threadIdx.x - 192; e < kND * kNK / 4; e += 128)
-          reinterpret_cast<float4*>(pv)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (owner) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { s_sum[q * 64 + 16 * j + lane] = mys[j]; mys[j] = 0.f; }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 192;
-      if (e < 64)
-        a.part_s[(long long)(b * a.P + pidx) * kNK + e] = s_sum[e] + s_sum[64 + e] + s_sum[128 + e] + s_sum[192 + e];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
-  }
-}
-
-
 // ===========================================================================================================
-// Pipelined variant (default).  netvlad_tc_kernel above runs each 64-point tile as one serial chain
-// (split -> logits MMAs -> softmax -> residual MMAs; ~14000 cycles per tile, ncu r1j) because its single xh/xl
-// operand tile is shared by both products and there is no room for a second one next to the raw ring.
-// Here the raw fp32 slabs are converted IN PLACE: two raw slabs [64 rows x 32 fp32] of 8 KB (features 64j..64j+63)
+// The kernel.  A first version ran each 64-point tile as one serial chain (split -> logits MMAs -> softmax ->
+// residual MMAs; ~14000 cycles per tile, ncu r1j: 239 us per 32 x 8192 points) because its single xh/xl operand tile
+// was shared by both products and there was no room for a second one next to an 8-slab raw ring; it was deleted once
+// this one measured 150 us (profiles/op_table_r1z.json vs r2a).  Here the raw fp32 slabs are converted IN PLACE: two raw slabs [64 rows x 32 fp32] of 8 KB (features 64j..64j+63)
 // become the xh slab and the xl slab [64 rows x 64 fp16] of the same 16 KB, and every thread reads and writes
 // only its own 128-byte rows, so the conversion needs no extra synchronisation.  That frees the 64 KB of xh/xl
 // and turns the raw ring into TWO whole-tile buffers: tile i+1 is loaded and split while tile i is in the tensor
@@ -779,16 +492,6 @@ int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, 
   if ((rc = nv_make_map_f16(&mh, base, kNK, kND, kND, kNK)) != DH3D_OK) return rc;
   if ((rc = nv_make_map_f16(&ml, base + plane, kNK, kND, kND, kNK)) != DH3D_OK) return rc;
   NvArgs a{att, reinterpret_cast<const float*>(base + 2 * plane), bn_scale, bn_shift, part_v, part_s, N, tpc, nf, P};
-  // DH3D_NETVLAD_PIPE=0 selects the serial-chain kernel (A/B comparison); default = in-place split, two tile buffers
-  static const bool serial = getenv("DH3D_NETVLAD_PIPE") && getenv("DH3D_NETVLAD_PIPE")[0] == '0';
-  if (serial) {
-    const int smem = (int)NvSmem::total + 1024;
-    cudaError_t e = cudaFuncSetAttribute(netvlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    netvlad_tc_kernel<<<dim3(C, B), kNThreads, smem, st>>>(mx, mh, ml, a);
-    if (P_out) *P_out = P;
-    return launch_status();
-  }
   const int smem = (int)NvSmem2::total + 1024;
   cudaError_t e = cudaFuncSetAttribute(netvlad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;

@@ -1,4 +1,4 @@
-// Shared pieces of the tcgen05 kernels (gemm_tc.cu, flexconv_tc.cu): TMA / UMMA / TMEM PTX wrappers,
+// Shared pieces of the tcgen05 kernels (gemm_tc16.cu, flexconv_ca.cu, netvlad_tc.cu): TMA / UMMA / TMEM PTX wrappers,
 // the 128B-swizzle K-major shared-memory descriptor, and the host-side tensor-map encoder.
 #pragma once
 #include <cuda.h>

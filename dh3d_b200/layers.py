@@ -24,8 +24,9 @@ from . import ops, user_ops
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID
 
 def use_tensor_cores():
-    """DH3D_GEMM=simt selects the exact-fp32 FFMA GEMMs; default is the tcgen05 3xTF32 path."""
-    return not os.environ.get("DH3D_GEMM", "tc").lower().startswith("s")
+    """DH3D_EXACT_FP32=1 -- the library's one process-wide switch (csrc/capi.cu) -- selects the exact-fp32 debug
+    path (FFMA GEMMs, two-kernel FlexConv, FFMA NetVLAD); default is the tcgen05 kernels."""
+    return os.environ.get("DH3D_EXACT_FP32", "0") in ("", "0")
 
 
 TENSORPACK_BN_EPS = 1e-5  # tensorpack BatchNorm default epsilon (library default; parity unpinned)
@@ -161,8 +162,7 @@ class FlexConvolution(FoldedModule):
             fb = None if self.feature_bias is None else self.feature_bias.reshape(-1).contiguous()
             # weight-only operand prepared once (dh3d_flex_conv_prepack): no per-forward packing launches
             packed = (ops.flex_conv_prepack(self.position_theta, self.position_bias, fb, scale, shift)
-                      if self.position_theta.is_cuda and os.environ.get("DH3D_FLEXCONV_PREPACK", "1") != "0"
-                      else None)
+                      if self.position_theta.is_cuda else None)
             self._folded = (fb, scale, shift, packed)
         fb, scale, shift, packed = self._folded
         if packed is not None:

@@ -98,8 +98,9 @@ DH3D_API int dh3d_flex_conv_pm(const float* features_pm, const float* theta, con
  * core/tf_utils.py:58-63): dh3d_flex_conv_prepack derives, once per layer, the contraction operand
  * [position_bias; theta_x; theta_y; theta_z] in the kernel's layout plus the folded shift
  * feature_bias*scale + shift; dh3d_flex_conv_pm_packed is dh3d_flex_conv_pm on that buffer (pass the SAME
- * scale).  packed: dh3d_flex_conv_prepack_bytes(Din, Dout) bytes, 256-byte aligned; it depends on the
- * DH3D_GEMM / DH3D_FLEXCONV settings of the process that made it. */
+ * scale).  packed: dh3d_flex_conv_prepack_bytes(Din, Dout) bytes, 256-byte aligned.  The buffer holds the operand
+ * in every form a kernel may read (plain fp32 for the two-kernel FFMA form, {hi^T, lo^T} tf32 pairs for the fused
+ * tcgen05 kernel), so it does not depend on any setting of the process that made it. */
 DH3D_API size_t dh3d_flex_conv_prepack_bytes(int Din, int Dout);
 DH3D_API int dh3d_flex_conv_prepack(const float* theta, const float* bias, const float* feature_bias,
                            const float* scale, const float* shift, int Din, int Dout, void* packed,
@@ -184,9 +185,11 @@ DH3D_API int dh3d_three_interpolate_from_dist(int b, int m, int c, int n, const 
  * ------------------------------------------------------------------------------------------- */
 DH3D_API int dh3d_linear(const float* x, int ldx, const float* w, const float* scale, const float* shift,
                 int act, float* y, int ldy, int M, int K, int N, void* stream);
-/* Tensor-core path of dh3d_linear (tcgen05.mma kind::tf32 with the 3xTF32 hi/lo split: fp32-grade
- * accuracy, ~1e-6 relative).  The weight is pre-split ONCE into packed = {W_hi^T, W_lo^T} ([N,K]
- * K-major, what the UMMA descriptors want); activations are split on the fly in shared memory. */
+/* Tensor-core path of dh3d_linear: tcgen05.mma kind::f16 on 2-term fp16 splits (22 mantissa bits, 3 MMAs per
+ * product; ~3e-5 * rms against fp64, inside the 1e-4 bar).  The weight is pre-split ONCE into packed =
+ * {W_hi^T, W_lo^T, per-column scale} ([N,K] K-major, what the UMMA descriptors want); activations are split on the
+ * fly in shared memory with a fixed 2^4 scale, and rows whose largest |x| leaves [2^-11, 3750] (or hold inf / NaN)
+ * are recomputed in fp32 by the same launch: any finite activation magnitude is accurate (csrc/gemm_tc16.cu). */
 DH3D_API size_t dh3d_linear_prepack_bytes(int K, int N);
 DH3D_API int dh3d_linear_prepack(const float* w, int K, int N, void* packed, void* stream);
 DH3D_API int dh3d_linear_packed(const float* x, int ldx, const void* packed_w, const float* scale,
@@ -202,9 +205,9 @@ DH3D_API int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* pack
  * core/model.py:177-181 in one launch:
  *     y  = act_a((xa @ Wa)*scale_a + shift_a) + act_b((xb @ Wb)*scale_b + shift_b)          [M,N]
  *     yn = y / sqrt(max(sum_n y^2, eps))      (y_normalized may be NULL)
- * packed_wa / packed_wb come from dh3d_linear_prepack (fp16-pair layout, the default).  N must be 128 (the row
- * norm needs the whole output row in one tile); otherwise, or with DH3D_GEMM_SPLIT=tf32, DH3D_ERR_UNSUPPORTED and
- * the caller composes dh3d_linear_packed x2 + dh3d_add_l2_normalize_rows. */
+ * packed_wa / packed_wb come from dh3d_linear_prepack.  N must be 128 (the row norm needs the whole output row
+ * in one tile); otherwise DH3D_ERR_UNSUPPORTED and the caller composes dh3d_linear_packed x2 +
+ * dh3d_add_l2_normalize_rows. */
 DH3D_API int dh3d_linear_join_packed(const float* xa, int ldxa, const void* packed_wa, const float* scale_a,
                             const float* shift_a, int act_a, const float* xb, int ldxb,
                             const void* packed_wb, const float* scale_b, const float* shift_b, int act_b,

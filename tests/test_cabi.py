@@ -88,10 +88,9 @@ def test_argument_validation_happens_before_any_cuda_call():
 
 def test_workspace_queries():
     lib = _lib.lib()
-    # sorted float4 points + one (min,max) float4 pair per 32-point chunk + one pair per 16 chunks; never
-    # less than the exhaustive tiled path (DH3D_KNN=tiled) needs
+    # sorted float4 points + one (min,max) float4 pair per 32-point chunk + one pair per 16 chunks
     assert lib.dh3d_knn_workspace_bytes(2, 8192) == 2 * (8192 * 16 + 256 * 32 + 16 * 32)
-    assert lib.dh3d_knn_workspace_bytes(1, 4) == 1024 * 16
+    assert lib.dh3d_knn_workspace_bytes(1, 4) == 32 * 16 + 1 * 32 + 1 * 32      # one padded chunk, one super-chunk
     assert lib.dh3d_knn_workspace_bytes(1, 9000) == 9024 * 16 + 282 * 32 + 18 * 32
     assert lib.dh3d_flex_conv_pm_workspace_bytes(1, 128, 8, 32, 64) >= 128 * 4 * 32 * 4 + 4 * 32 * 64 * 4
     assert lib.dh3d_flex_conv_workspace_bytes(1, 32, 4, 2, 6) > 0     # padded odd dims are accepted

@@ -1,5 +1,5 @@
-"""GPU tests of the tcgen05 GEMM path (default: fp16-pair split on kind::f16, gemm_tc16.cu; DH3D_GEMM_SPLIT=tf32:
-3xTF32, gemm_tc.cu) against fp64 and against the exact-fp32 FFMA path."""
+"""GPU tests of the tcgen05 GEMM path (fp16-pair split on kind::f16, gemm_tc16.cu; formerly also a 3xTF32 variant:
+3xTF32, deleted) against fp64 and against the exact-fp32 FFMA path."""
 import numpy as np
 import pytest
 import torch
@@ -169,27 +169,38 @@ def test_non_finite_rows_stay_confined_to_their_row():
 
 
 @pytest.mark.timeout(600)
-def test_tf32_split_path_in_subprocess():
-    """DH3D_GEMM_SPLIT is read once per process: run this file's accuracy tests on the 3xTF32 kernels."""
+def test_exact_fp32_debug_path_in_subprocess():
+    """DH3D_EXACT_FP32=1 (the library's one process-wide switch, read once): the FFMA GEMMs / two-kernel FlexConv /
+    FFMA NetVLAD must pass the same accuracy tests, and a weight buffer prepacked under either setting is the same
+    bytes (no layout depends on the switch)."""
     import os
     import subprocess
     import sys
-    if os.environ.get("DH3D_GEMM_SPLIT") == "tf32":
-        pytest.skip("already the tf32 run")
-    env = dict(os.environ, DH3D_GEMM_SPLIT="tf32")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
-                        "vs_fp64 or rowdot or strided"], env=env, capture_output=True, text=True)
+    if os.environ.get("DH3D_EXACT_FP32", "0") not in ("", "0"):
+        pytest.skip("already the exact-fp32 run")
+    env = dict(os.environ, DH3D_EXACT_FP32="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_ops_gpu.py"),
+                        os.path.join(here, "test_model_gpu.py"), "-k",
+                        "flex_conv_pm_vs_fp64_truth or fused_epilogue or netvlad_vs_fp64 or linear_vs_fp64 or "
+                        "matches_oracle_small or prepacked_is_bit_identical"],
+                       env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    code = ("import torch, hashlib, sys; sys.path.insert(0, %r); from dh3d_b200 import ops; g = torch.Generator().manual_seed(0);"
+            "th = torch.randn((3, 64, 128), generator=g).cuda(); bi = torch.randn((64, 128), generator=g).cuda();"
+            "p = ops.flex_conv_prepack(th, bi); torch.cuda.synchronize(); print(hashlib.sha1(p.cpu().numpy().tobytes()).hexdigest())"
+            % os.path.dirname(here))
+    a = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    b = subprocess.run([sys.executable, "-c", code], env=dict(os.environ), capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr[-800:] + b.stderr[-800:]
+    assert a.stdout.strip() == b.stdout.strip()
 
 
 @pytest.mark.parametrize("M,Ka,Kb", [(1000, 192, 64), (128 * 149 + 5, 192, 64), (300, 64, 32), (4096, 36, 192)])
 def test_linear_join_vs_fp64_and_unfused(M, Ka, Kb):
     """dh3d_linear_join_packed: relu(BN(xa@Wa)) + relu(BN(xb@Wb)) and its l2-normalised rows in one launch
     (core/backbones.py:121-123 + core/model.py:177-181) against fp64 and against the separate launches."""
-    import os
     from dh3d_b200 import ops
-    if os.environ.get("DH3D_GEMM_SPLIT") == "tf32":
-        pytest.skip("the join kernel exists for the fp16-pair layout only (callers compose the separate ops)")
     rng = np.random.RandomState(M + Ka)
     N = 128
     xa, xb = rng.randn(M, Ka).astype(np.float32), rng.randn(M, Kb).astype(np.float32)

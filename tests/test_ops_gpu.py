@@ -258,22 +258,6 @@ def test_flex_conv_prepacked_is_bit_identical_to_the_per_call_form():
         assert torch.equal(a0, b0)
 
 
-@pytest.mark.timeout(600)
-@pytest.mark.parametrize("mode", ["regs", "split", "g4"])
-def test_flex_conv_other_kernels_in_subprocess(mode):
-    """DH3D_FLEXCONV is read once per process: run the FlexConv accuracy tests on the per-thread-gather fused
-    kernel (flexconv_tc.cu), the TMA gather4 kernel (flexconv_g4.cu) and the two-kernel form as well (default =
-    cp.async staging, flexconv_ca.cu)."""
-    import subprocess
-    import sys
-    if os.environ.get("DH3D_FLEXCONV"):
-        pytest.skip("already a non-default FlexConv run")
-    env = dict(os.environ, DH3D_FLEXCONV=mode)
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k",
-                        "flex_conv_pm_vs_fp64_truth or fused_epilogue"], env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-
-
 def test_flex_conv_centre_is_the_point_itself_on_duplicates():
     """Duplicated points: nbr(0,n) may differ from n; the CUDA reference centres on p[n]
     (flex_conv_kernel_gpu.cu.cc:75-79), and p[nbr0] == p[n] anyway for exact duplicates."""
@@ -417,19 +401,6 @@ def test_netvlad_vs_fp64(B, N):
     close(out, net.netvlad(feat, att, p, final_l2norm=True))
     raw = blk(None, cu(feat), cu(att), final_l2norm=False)
     close(raw, net.netvlad(feat, att, p, final_l2norm=False))
-
-
-@pytest.mark.timeout(300)
-def test_netvlad_simt_kernel_and_degenerate_rows_in_subprocess():
-    """DH3D_NETVLAD is read once per process: the FFMA aggregation kernel (netvlad.cu) must still pass."""
-    import subprocess
-    import sys
-    if os.environ.get("DH3D_NETVLAD"):
-        pytest.skip("already the simt run")
-    env = dict(os.environ, DH3D_NETVLAD="simt")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", __file__, "-k", "netvlad_vs_fp64"],
-                       env=env, capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_netvlad_tiny_and_huge_feature_norms():

@@ -210,17 +210,23 @@ netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
-#pragma unroll 4
-  for (int r = 0; r < kVSlice; r += 4) {   // one broadcast LDS.128 feeds four FMAs (was one LDS per FMA)
-    const float w0 = __ldg(w + (long long)r * kVD), w1 = __ldg(w + (long long)(r + 1) * kVD),
-                w2 = __ldg(w + (long long)(r + 2) * kVD), w3 = __ldg(w + (long long)(r + 3) * kVD);
+  // the weight stream is what this kernel waits for (64 KB per CTA, read once per batch): 16 coalesced row loads in
+  // flight per thread (4 rounds of latency instead of 16; r2: 35 -> see profiles/op_table_r2*.json)
+#pragma unroll 1
+  for (int r0 = 0; r0 < kVSlice; r0 += 16) {
+    float wv[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float4 x = *reinterpret_cast<const float4*>(&s_x[i][r]);
-      acc[i] = fmaf(x.x, w0, acc[i]);
-      acc[i] = fmaf(x.y, w1, acc[i]);
-      acc[i] = fmaf(x.z, w2, acc[i]);
-      acc[i] = fmaf(x.w, w3, acc[i]);
+    for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + (long long)(r0 + j) * kVD);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(&s_x[i][r0 + j]);   // broadcast LDS.128 feeds four FMAs
+        acc[i] = fmaf(x.x, wv[j], acc[i]);
+        acc[i] = fmaf(x.y, wv[j + 1], acc[i]);
+        acc[i] = fmaf(x.z, wv[j + 2], acc[i]);
+        acc[i] = fmaf(x.w, wv[j + 3], acc[i]);
+      }
     }
   }
   for (int i = 0; i < nb; ++i)
@@ -245,7 +251,7 @@ netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B, const f
     if (lane == 0) s_g[warp] = t;
   }
   float h = 0.f;
-#pragma unroll 16
+#pragma unroll 32
   for (int s = 0; s < slices; ++s) h += part_h[((long long)s * B + b) * kVD + tid];
   __syncthreads();
   h *= rsqrtf(fmaxf(s_g[0] + s_g[1], 1e-12f));
@@ -253,7 +259,7 @@ netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B, const f
   s_h[tid] = h;
   __syncthreads();
   float g = 0.f;
-#pragma unroll 16
+#pragma unroll 32
   for (int i = 0; i < kVD; ++i) g = fmaf(s_h[i], __ldg(gw + i * kVD + tid), g);
   g = fmaf(g, __ldg(g_scale + tid), __ldg(g_shift + tid));
   float y = h * (1.f / (1.f + __expf(-g)));

@@ -56,7 +56,11 @@ def test_linear_packed_strided_output_and_exact_small_values():
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("M,K,N", [(1000, 256, 1024), (262144, 128, 64), (333, 64, 16), (4096, 512, 256)])
+@pytest.mark.parametrize("M,K,N", [(1000, 256, 1024), (262144, 128, 64), (333, 64, 16), (4096, 512, 256),
+                                   # paired-CTA (multicast) launches: odd tile counts, ragged last tile, 1..8 K slabs,
+                                   # 2..8 N tiles
+                                   (5000, 256, 1024), (4096 + 77, 96, 256), (128 * 33, 32, 384), (40000, 256, 1024),
+                                   (128 * 297 + 1, 160, 512)])
 def test_linear_rowdot_fused_head(M, K, N):
     from dh3d_b200 import ops
     x, w, sc, sh = _case(M, K, N, 7 * M + N)
@@ -126,15 +130,17 @@ def test_out_of_window_rows_are_recomputed_in_fp32_all_three_kernels():
         e = x.astype(np.float64) @ w.astype(np.float64)
         assert np.isfinite(y).all()
         assert _rowwise_rel_err(y, e) < 1e-4, (N, _rowwise_rel_err(y, e))
-    # fused head: relu(x @ W) . w2 -> compare the pre-sigmoid logit through a linear final activation
+    # fused head: relu(x @ W) . w2 -> compare the pre-sigmoid logit through a linear final activation; 1500 rows run
+    # single CTAs, 6000 rows the paired-CTA (multicast) launch
     N = 1024
     w = (rng.randn(K, N) / np.sqrt(K)).astype(np.float32)
     w2 = (rng.randn(N) / np.sqrt(N)).astype(np.float32)
-    yd = ops.linear_rowdot(t(x), ops.linear_prepack(t(w)), None, None, 1, t(w2), 0.0, 0).cpu().numpy()
-    h = np.maximum(x.astype(np.float64) @ w.astype(np.float64), 0)
-    ed = h @ w2.astype(np.float64)
-    scale = np.sqrt((h ** 2).mean(axis=1)) * np.sqrt((w2.astype(np.float64) ** 2).sum())   # size of the terms summed
-    assert np.isfinite(yd).all() and (np.abs(yd - ed) / (scale + 1e-300)).max() < 1e-4
+    for xx in (x, _range_case(21, 6000, K)):
+        yd = ops.linear_rowdot(t(xx), ops.linear_prepack(t(w)), None, None, 1, t(w2), 0.0, 0).cpu().numpy()
+        h = np.maximum(xx.astype(np.float64) @ w.astype(np.float64), 0)
+        ed = h @ w2.astype(np.float64)
+        scale = np.sqrt((h ** 2).mean(axis=1)) * np.sqrt((w2.astype(np.float64) ** 2).sum())   # size of the terms summed
+        assert np.isfinite(yd).all() and (np.abs(yd - ed) / (scale + 1e-300)).max() < 1e-4
     # join
     xa, xb = _range_case(11, M, 192), _range_case(12, M, 64)
     wa, wb = (rng.randn(192, 128) / 14).astype(np.float32), (rng.randn(64, 128) / 8).astype(np.float32)

@@ -18,8 +18,14 @@
 // IMNMX per element on the first N pass and a never-taken branch; out-of-distribution clouds cost
 // ~3 us per affected row instead of poisoning the descriptors (round-1 ADVICE / VERDICT item 5).
 //
-// Persistent warp-specialised structure (320 threads, one CTA per SM, 2-CTA
-// clusters multicasting the W tiles), with
+// Persistent warp-specialised structure (320 threads, one CTA per SM).  With enough M tiles the CTAs run as PAIRS
+// (MC = 2, one thread-block cluster per TPC) issuing tcgen05.mma.cta_group::2: the pair's accumulator is 256 rows x BN
+// (each CTA's 128 rows in its own TMEM), each CTA stages its own X tile and only its N HALF of the W tile, and the
+// leader CTA's MMA thread issues for both.  A single-CTA 128 x 256 x 16 MMA reads 4 KB of A + 8 KB of B from shared
+// memory per 128 tensor cycles = 96 of the SM's 128 B/clk, and with the TMA writes and the split warps' traffic on
+// top the 256 -> 1024 heads were SHARED-MEMORY-bandwidth bound at 66 % tensor-pipe activity (ncu r1s/r2j: 152 KB of
+// shared-memory traffic per K slab vs 768 MMA cycles); the pair form reads 4 + 4 KB per MMA and stages half the W
+// bytes per CTA (112 KB per slab).  Structure:
 //   * K slabs of 32: raw X tile [128 x 32] fp32 (TMA, 128B swizzle) -> warps 2-5 write xh / xl as
 //     [128 x 32] fp16 tiles in the 64B-swizzled K-major layout (conflict-free 16-byte loads/stores);
 //     W_h^T / W_l^T tiles [BN x 32] fp16 arrive by TMA in that layout (pre-split once per weight);
@@ -69,17 +75,22 @@ __device__ __forceinline__ void t16_queue_bad_rows(uint32_t (&rmax)[4], int t, i
   }
 }
 
-template <int BN>
+template <int BN, int MC>
 struct T16Cfg {
-  static constexpr int kStages = BN >= 256 ? 3 : 4;
+  // one stage = the X slab [128 x 32] (16 KB: raw fp32 from TMA, then its xh | xl fp16 halves written IN PLACE by the
+  // split warps) + this CTA's W_h / W_l slices; as many stages as fit in 192 KB, at most 6
   static constexpr uint32_t kRawBytes = kTcBM * kTcBK * 4;   // 16 KB fp32, SW128
   static constexpr uint32_t kABytes = kTcBM * kTcBK * 2;     // 8 KB fp16, SW64
-  static constexpr uint32_t kBBytes = BN * kTcBK * 2;
-  static constexpr uint32_t kStageBytes = kRawBytes + 2 * kABytes + 2 * kBBytes;
+  static constexpr uint32_t kBBytes = (BN / MC) * kTcBK * 2; // a CTA of a pair holds its N half of the W tile
+  static constexpr uint32_t kStageBytes = kRawBytes + 2 * kBBytes;
+  static constexpr int kStages = (192u * 1024u) / kStageBytes < 6 ? (int)((192u * 1024u) / kStageBytes) : 6;
   static constexpr uint32_t kParamBytes = 2 * 3 * BN * 4;    // double-buffered scale/shift/w2 slices
   static constexpr uint32_t kSmemBytes =
       kStages * kStageBytes + kTcStageOutBytes + kParamBytes + 256 /*barriers*/ + kT16BadBytes + 1024 /*align*/;
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(kABytes * 2 == kRawBytes, "the fp16 pair replaces the raw slab in place");
+  static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
+  static_assert((3 * kStages + 4) * 8 + 8 <= 256, "barrier block");
 };
 
 struct T16Epilogue {
@@ -275,16 +286,60 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   return d;
 }
 
+// CG = 2: one instruction for the CTA pair (issued by the leader): each CTA's A tile [128 x 16] and N half of the
+// B tile at the SAME shared-memory offsets in both CTAs, D rows 0-127 in the leader's TMEM, 128-255 in the peer's.
+template <int CG = 1>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// barrier helpers of the pair form: arrives go to the LEADER CTA's barrier (rank 0 of the cluster), commits are multicast
+// to both CTAs.  The arrive keeps the default (.release.cta) semantics: what it orders are the arriving thread's own
+// shared-memory writes, already made visible to the async proxy by its fence.proxy.async, and its tcgen05.ld's (fenced
+// by tcgen05.fence::before_thread_sync) -- an explicit .release.cluster / .acquire.cluster pair compiles to MEMBAR.ALL.GPU
+// + ERRBAR per arrive and CCTL.IVALL per wait (ncu source view: 20 % of the kernel's stall samples, 0.33 -> 0.48 ms).
+template <int MC>
+__device__ __forceinline__ void mbar_arrive_x(uint64_t* bar) {
+  if constexpr (MC == 1) {
+    mbar_arrive(bar);
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}" ::"r"(smem_u32(bar))
+        : "memory");
+  }
+}
+template <int MC>
+__device__ __forceinline__ void umma_commit_x(uint64_t* bar) {
+  if constexpr (MC == 1)
+    umma_commit(bar);
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
 }
 
 // 8 consecutive fp32 -> 8 fp16 high parts + 8 fp16 low parts (of x * 2^4), packed as two uint4
@@ -309,7 +364,7 @@ __global__ void __launch_bounds__(kT16Threads, 1)
 gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                  const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmY,
                  const T16Epilogue ep, int M, int K, int N) {
-  using Cfg = T16Cfg<BN>;
+  using Cfg = T16Cfg<BN, MC>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment computed on the shared-window address so the pointer keeps its state space (LDS/STS)
@@ -317,11 +372,13 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* out_stage = smem + S * Cfg::kStageBytes;                       // 4 x 4 KB, 1024-aligned
   float* params = reinterpret_cast<float*>(out_stage + kTcStageOutBytes);  // [2][3][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);
+  // MC == 2: conv and tmem_empty are only used in the LEADER CTA (rank 0; its MMA thread issues for the pair), the
+  // peer's split / epilogue warps arrive there remotely; the leader's commits are multicast to both CTAs.
   uint64_t* full = bars;            // TMA bytes landed                 (count 1 + tx)
-  uint64_t* conv = bars + S;        // xh / xl written                  (count 128)
-  uint64_t* empty = bars + 2 * S;   // MMAs reading the stage finished  (count MC, tcgen05.commit)
+  uint64_t* conv = bars + S;        // xh / xl written                  (count 4 * MC, one per split warp)
+  uint64_t* empty = bars + 2 * S;   // MMAs reading the stage finished  (count 1, tcgen05.commit)
   uint64_t* tmem_full = bars + 3 * S;       // [2] accumulator ready    (count 1, tcgen05.commit)
-  uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] accumulator drained  (count 4, one per epilogue warp)
+  uint64_t* tmem_empty = bars + 3 * S + 2;  // [2] accumulator drained  (count 4 * MC, one per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
   uint32_t* bad = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [0] count, [4..] rows
 
@@ -334,36 +391,40 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int mt_stride = (int)gridDim.x;
 
   auto stage_raw = [&](int s) { return smem + s * Cfg::kStageBytes; };
-  auto stage_ah = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes; };
-  auto stage_al = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + Cfg::kABytes; };
-  auto stage_bh = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes; };
-  auto stage_bl = [&](int s) {
-    return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + 2 * Cfg::kABytes + Cfg::kBBytes;
-  };
+  auto stage_ah = [&](int s) { return smem + s * Cfg::kStageBytes; };                  // over the raw slab
+  auto stage_al = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kABytes; };
+  auto stage_bh = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes; };
+  auto stage_bl = [&](int s) { return smem + s * Cfg::kStageBytes + Cfg::kRawBytes + Cfg::kBBytes; };
 
   if (threadIdx.x == 0) {
     bad[0] = 0u;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 128);
-      mbar_init(&empty[s], MC);  // one tcgen05.commit per CTA of the cluster (peers write this stage too)
+      mbar_init(&conv[s], 4 * MC);
+      mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 4 * MC);
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "r"(Cfg::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // both CTAs of a pair allocate (same warp, same slot address)
+    if constexpr (MC == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if constexpr (MC > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast
+  if constexpr (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / commit
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -380,26 +441,17 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&full[s], Cfg::kRawBytes + 2 * Cfg::kBBytes);
             tma_load_2d(stage_raw(s), &tmA, kb * kTcBK, mt * kTcBM, &full[s]);
-            if constexpr (MC == 1) {
-              tma_load_2d(stage_bh(s), &tmBh, kb * kTcBK, nt * BN, &full[s]);
-              tma_load_2d(stage_bl(s), &tmBl, kb * kTcBK, nt * BN, &full[s]);
-            } else {
-              // this CTA's half of the W tile (rows crank*BN/2 ..) lands in BOTH CTAs' stage s
-              constexpr int HB = BN / MC;
-              const uint32_t off = crank * HB * (kTcBK * 2);
-              tma_load_2d_mc(stage_bh(s) + off, &tmBh, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
-                             (uint16_t)((1u << MC) - 1));
-              tma_load_2d_mc(stage_bl(s) + off, &tmBl, kb * kTcBK, nt * BN + (int)crank * HB, &full[s],
-                             (uint16_t)((1u << MC) - 1));
-            }
+            // this CTA's N slice of the W tile (the whole tile for MC == 1)
+            tma_load_2d(stage_bh(s), &tmBh, kb * kTcBK, nt * BN + (int)crank * (BN / MC), &full[s]);
+            tma_load_2d(stage_bl(s), &tmBl, kb * kTcBK, nt * BN + (int)crank * (BN / MC), &full[s]);
           }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N, M=128
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+    if (lane == 0 && crank == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N, M = 128 per CTA of the group
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((kTcBM * MC) >> 4) << 24);
       uint32_t it = 0, tile = 0;
       for (int mtb = mt_begin; mtb < num_mt; mtb += mt_stride)
         for (int nt = 0; nt < num_nt; ++nt, ++tile) {
@@ -419,14 +471,13 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kTcBK / 16; ++k) {
               const uint64_t off = (uint64_t)(k * 16 * 2) >> 4;  // 32 bytes per K=16 step, 16-byte units
-              umma_f16(tmem_d, a_l + off, b_h + off, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_f16(tmem_d, a_h + off, b_l + off, idesc, 1u);
-              umma_f16(tmem_d, a_h + off, b_h + off, idesc, 1u);
+              umma_f16<MC>(tmem_d, a_l + off, b_h + off, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16<MC>(tmem_d, a_h + off, b_l + off, idesc, 1u);
+              umma_f16<MC>(tmem_d, a_h + off, b_h + off, idesc, 1u);
             }
-            if constexpr (MC == 1) umma_commit(&empty[s]);
-            else umma_commit_mc(&empty[s], (uint16_t)((1u << MC) - 1));  // frees the stage in every CTA
+            umma_commit_x<MC>(&empty[s]);   // frees the stage in both CTAs of a pair
           }
-          umma_commit(&tmem_full[acc]);
+          umma_commit_x<MC>(&tmem_full[acc]);
         }
     }
   } else if (warp < 6) {
@@ -447,20 +498,27 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint8_t* raw = stage_raw(s);
           uint8_t* ah = stage_ah(s);
           uint8_t* al = stage_al(s);
+          float4 v0[4], v1[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = (t >> 2) + 32 * i;
-            const float4 v0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
-            const float4 v1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
-            if (nt == 0) rmax[i] = t16_absmax8(rmax[i], v0, v1);   // the later N passes re-read the same rows
+            v0[i] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c) ^ (r & 7)) << 4));
+            v1[i] = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * c + 1) ^ (r & 7)) << 4));
+            if (nt == 0) rmax[i] = t16_absmax8(rmax[i], v0[i], v1[i]);   // the later N passes re-read the same rows
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");   // every split thread holds its part of the raw slab
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (t >> 2) + 32 * i;
             uint4 hi, lo;
-            split8(v0, v1, hi, lo);
+            split8(v0[i], v1[i], hi, lo);
             const uint32_t off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
             *reinterpret_cast<uint4*>(ah + off) = hi;
             *reinterpret_cast<uint4*>(al + off) = lo;
           }
           fence_proxy_async();
-          mbar_arrive(&conv[s]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_x<MC>(&conv[s]);
         }
         if (nt == 0) t16_queue_bad_rows(rmax, t, (mtb + (int)crank) * kTcBM, bad);
       }
@@ -497,7 +555,7 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c0 + 32 >= BN) {  // accumulator fully read: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) mbar_arrive_x<MC>(&tmem_empty[acc]);
           }
           float v[32];
 #pragma unroll
@@ -538,9 +596,12 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (MC > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(Cfg::kTmemCols)
-                 : "memory");
+    if constexpr (MC == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                   : "memory");
   }
   // out-of-window rows (never in-distribution): fp32 recompute over the tensor-core result; every TMA store of
   // this CTA has completed (epilogue warps waited on their bulk groups before the barrier above)
@@ -635,7 +696,7 @@ static int launch_t16_mc(const float* x, int ldx, const __half* wh, const __half
   else if ((rc = make_map(&my, y, M, N, ldy, 32)) != DH3D_OK) return rc;
   auto kern = gemm_tc16_kernel<BN, ROWDOT, MC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)T16Cfg<BN>::kSmemBytes);
+                                       (int)T16Cfg<BN, MC>::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   const int num_mt = ceil_div(M, kTcBM);
   int grid = num_mt < num_sms() ? num_mt : num_sms();
@@ -644,7 +705,7 @@ static int launch_t16_mc(const float* x, int ldx, const __half* wh, const __half
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kT16Threads);
-  cfg.dynamicSmemBytes = T16Cfg<BN>::kSmemBytes;
+  cfg.dynamicSmemBytes = T16Cfg<BN, MC>::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -215,7 +215,7 @@ def algorithmic(tag, name):
 
 # C-ABI entry point -> the kernel that dominates it (prefix of the ncu kernel name), for roofline.traffic
 OP_KERNEL = {
-    "dh3d_linear_rowdot_packed": ("gemm_tc16_kernel",),
+    "dh3d_linear_rowdot_packed": ("gemm_head16_kernel", "gemm_tc16_kernel"),
     "dh3d_linear_packed": ("gemm_tc16_kernel",),
     "dh3d_netvlad": ("netvlad_tc2_kernel", "netvlad_tc_kernel"),
     "dh3d_knn_bruteforce_pm": ("knn_query_kernel<8, 1, 1",),

@@ -35,6 +35,14 @@ USE_FUSED_BLOCKS = True
 class DilateGeometry(object):
     """Everything ``flex_conv_dilate(dilate > 1)`` derives from xyz alone."""
 
+    ready = None   # event recorded on the stream that computed the geometry (DH3D.forward's side stream)
+
+    def join(self):
+        """Makes the current stream wait for the geometry (once); a no-op when it was computed on this stream."""
+        if self.ready is not None:
+            torch.cuda.current_stream(self.kp_indices.device).wait_event(self.ready)
+            self.ready = None
+
     def __init__(self, xyz, npoint, knn):
         self.kp_indices = ops.farthest_point_sample(npoint, xyz)              # [B,M]
         self.points_sampled = ops.gather_point(xyz, self.kp_indices)          # [B,M,3]
@@ -114,6 +122,7 @@ class FlexConvDilate(nn.Module):
         into its first columns, so the channel concat of core/backbones.py:96-99 is never copied."""
         if self.dilate > 1:
             g = geometry or DilateGeometry(xyz, xyz.shape[1] // self.dilate, self.knn)
+            g.join()
             pts = g.points_sampled
             if cat is not None:
                 cin = cat.shape[2] - self.outdims[-1]

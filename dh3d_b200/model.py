@@ -76,10 +76,13 @@ class DH3D(nn.Module):
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
+                # the main stream joins where the geometry is first consumed (stage 2's group_point), so the
+                # k-NN of the sampled points and the 3-NN run next to stage 1 instead of in front of it
+                geometry.ready = torch.cuda.Event()
+                geometry.ready.record(self._side)
         if knn_inds is None:
             knn_inds, _ = ops.knn_points(points, c.knn_num)
         if overlap:
-            cur.wait_stream(self._side)
             if not torch.cuda.is_current_stream_capturing():
                 for t in (geometry.kp_indices, geometry.points_sampled, geometry.knn_indices,
                           geometry.nn_dist, geometry.nn_idx):
@@ -111,6 +114,8 @@ class DH3D(nn.Module):
                 gpoints, forglobal, _ = subsample(points, forglobal, c.global_subsample)
             att = self.globalatt(forglobal)
             out["globaldesc"] = self.netvlad(gpoints, forglobal, att, final_l2norm=True, out=given.get("globaldesc"))
+        if overlap:
+            geometry.join()   # (already joined by stage 2; keeps the side stream joined for configurations that skip it)
         if "xyz_feat" in want:
             out["xyz_feat"] = torch.cat([points, out["local_desc"]], dim=-1)
         if "xyz_feat_att" in want and c.detection:

@@ -34,9 +34,10 @@ __global__ void __launch_bounds__(kVD)
 netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict__ att, int N,
                          int slabs, const float* __restrict__ cw, const float* __restrict__ bn_scale,
                          const float* __restrict__ bn_shift, float* __restrict__ part_v,
-                         float* __restrict__ part_s) {
+                         float* __restrict__ part_s, unsigned int* zero_word) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VladSmem& sm = *reinterpret_cast<VladSmem*>(smem_raw);
+  if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0u;   // tail barrier counter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, slab = blockIdx.x;
   const int per = (N + slabs - 1) / slabs;
@@ -135,21 +136,38 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
   if (tid < kVK) part_s[((long long)b * slabs + slab) * kVK + tid] = ssum;
 }
 
-// CTA (b, q): clusters 16q .. 16q+15 of cloud b; thread = feature d.  Combines the slabs, subtracts S*W2,
-// intra-normalises each cluster column (over the 256 features, inside the CTA) and writes the feature-major
-// flattening ([d*64 + k], backbones.py:258-260).  The global l2 norm of the flattened vector only needs the 64
-// column norms: they go to coln[b][k] and the scalar is applied after the (linear) projection, in the head
-// kernel -- which lets four CTAs per cloud run here instead of one (r1o: 52 us for 32 CTAs, latency-bound).
+// ---- tail: slab combine + intra-norm -> 16384 x 256 projection -> BN / context gating / l2-norm, ONE launch ------------
+// Three phases of one persistent kernel (was three launches: 17 + 31 + 33 us for 32 clouds, each mostly launch ramp and
+// load latency), separated by grid barriers on a counter in the workspace (every CTA is resident: grid <= SM count,
+// one 256-thread CTA each).  Data written in one phase is read in the next with plain (coherent) loads.
 constexpr int kVQ = 16;
-__global__ void __launch_bounds__(kVD)
-netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restrict__ part_s, int slabs,
-                        const float* __restrict__ cw2, float* __restrict__ vlad, float* __restrict__ coln) {
+
+__device__ __forceinline__ void nv_grid_barrier(unsigned int* ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// phase A, work item (b, q): clusters 16q .. 16q+15 of cloud b; thread = feature d.  Combines the slabs, subtracts
+// S*W2, intra-normalises each cluster column (over the 256 features, inside the CTA) and writes the feature-major
+// flattening ([d*64 + k], backbones.py:258-260).  The global l2 norm of the flattened vector only needs the 64
+// column norms: they go to coln[b][k] and the scalar is applied after the (linear) projection, in phase C.
+__device__ __forceinline__ void nv_finalize_item(int b, int q, const float* __restrict__ part_v,
+                                                 const float* __restrict__ part_s, int slabs,
+                                                 const float* __restrict__ cw2, float* vlad, float* coln) {
   __shared__ float s_sum[kVQ];
   __shared__ float s_red[kVD / 32][kVQ];
   __shared__ float s_inv[kVQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x, k0 = blockIdx.y * kVQ;
-
+  const int k0 = q * kVQ;
+  __syncthreads();   // the previous item's readers of the shared arrays are done
   if (tid < kVQ) {
     float s = 0.f;
     for (int c = 0; c < slabs; ++c) s += part_s[((long long)b * slabs + c) * kVK + k0 + tid];
@@ -191,32 +209,35 @@ netvlad_finalize_kernel(const float* __restrict__ part_v, const float* __restric
         make_float4(v[k] * s_inv[k], v[k + 1] * s_inv[k + 1], v[k + 2] * s_inv[k + 2], v[k + 3] * s_inv[k + 3]);
 }
 
-// split-K projection: CTA s handles rows [s*64, s*64+64) of hidden1_weights [16384, 256] for a
-// group of up to 32 clouds; thread = output column.  part_h [slices][B][256].
-__global__ void __launch_bounds__(kVD)
-netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__ hw, int B, int KD,
-                       float* __restrict__ part_h) {
+// phase B, work item (slice, b0): split-K projection, rows [slice*64, slice*64+64) of hidden1_weights [16384, 256]
+// for the clouds b0 .. b0+31; thread = output column.  part_h [slices][B][256].
+__device__ __forceinline__ void nv_project_item(int slice, int b0, const float* vlad, const float* __restrict__ hw,
+                                                int B, int KD, float* part_h) {
   __shared__ __align__(16) float s_x[32][kVSlice];
   const int tid = threadIdx.x;
-  const int slice = blockIdx.x;
-  const int b0 = blockIdx.y * 32;
   const int nb = min(32, B - b0);
+  // the weight stream is what this phase waits for (64 KB per item, read once per batch): the first 16 coalesced row
+  // loads are issued before the activations are staged
+  const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
+  float wv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + (long long)j * kVD);
+  __syncthreads();   // the previous item's readers of s_x are done
   for (int i = tid; i < 32 * kVSlice; i += kVD) {
     const int bb = i / kVSlice, r = i % kVSlice;
-    s_x[bb][r] = bb < nb ? __ldg(vlad + (long long)(b0 + bb) * KD + (long long)slice * kVSlice + r) : 0.f;
+    s_x[bb][r] = bb < nb ? vlad[(long long)(b0 + bb) * KD + (long long)slice * kVSlice + r] : 0.f;   // written in phase A
   }
   __syncthreads();
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  const float* w = hw + ((long long)slice * kVSlice) * kVD + tid;
-  // the weight stream is what this kernel waits for (64 KB per CTA, read once per batch): 16 coalesced row loads in
-  // flight per thread (4 rounds of latency instead of 16; r2: 35 -> see profiles/op_table_r2*.json)
 #pragma unroll 1
   for (int r0 = 0; r0 < kVSlice; r0 += 16) {
-    float wv[16];
+    float wn[16];
+    if (r0 + 16 < kVSlice) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + (long long)(r0 + j) * kVD);
+      for (int j = 0; j < 16; ++j) wn[j] = __ldg(w + (long long)(r0 + 16 + j) * kVD);
+    }
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
 #pragma unroll
@@ -228,39 +249,49 @@ netvlad_project_kernel(const float* __restrict__ vlad, const float* __restrict__
         acc[i] = fmaf(x.w, wv[j + 3], acc[i]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) wv[j] = wn[j];
   }
   for (int i = 0; i < nb; ++i)
     part_h[((long long)slice * B + b0 + i) * kVD + tid] = acc[i];
 }
 
-// one CTA per cloud: sum slices, apply the global l2 norm of the flattened VLAD (from the column norms) ->
-// BN -> context gating (256x256 matvec, BN, sigmoid) -> optional final l2-normalise (core/model.py:205,
-// epsilon 1e-8).
-__global__ void __launch_bounds__(kVD)
-netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B, const float* __restrict__ coln,
-                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                    const float* __restrict__ gw, const float* __restrict__ g_scale,
-                    const float* __restrict__ g_shift, int final_l2norm, float* __restrict__ out) {
+// phase C, work item b: sum the slices, apply the global l2 norm of the flattened VLAD (from the column norms) ->
+// BN -> context gating (256x256 matvec, BN, sigmoid) -> optional final l2-normalise (core/model.py:205, eps 1e-8).
+__device__ __forceinline__ void nv_head_item(int b, const float* part_h, int slices, int B, const float* coln,
+                                             const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                             const float* __restrict__ gw, const float* __restrict__ g_scale,
+                                             const float* __restrict__ g_shift, int final_l2norm,
+                                             float* __restrict__ out) {
   __shared__ float s_h[kVD];
   __shared__ float s_red[kVD / 32];
   __shared__ float s_g[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
+  __syncthreads();
   if (tid < kVK) {
-    const float t = warp_sum(__ldg(coln + (long long)b * kVK + tid));
+    const float t = warp_sum(coln[(long long)b * kVK + tid]);
     if (lane == 0) s_g[warp] = t;
   }
-  float h = 0.f;
-#pragma unroll 32
-  for (int s = 0; s < slices; ++s) h += part_h[((long long)s * B + b) * kVD + tid];
+  float h4[4] = {0.f, 0.f, 0.f, 0.f};   // (four chains: the 256 partial rows are what this phase waits for)
+#pragma unroll 16
+  for (int s = 0; s < slices; s += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (s + u < slices) h4[u] += part_h[((long long)(s + u) * B + b) * kVD + tid];
+  }
+  float h = (h4[0] + h4[1]) + (h4[2] + h4[3]);
   __syncthreads();
   h *= rsqrtf(fmaxf(s_g[0] + s_g[1], 1e-12f));
   h = fmaf(h, __ldg(bn_scale + tid), __ldg(bn_shift + tid));
   s_h[tid] = h;
   __syncthreads();
-  float g = 0.f;
-#pragma unroll 32
-  for (int i = 0; i < kVD; ++i) g = fmaf(s_h[i], __ldg(gw + i * kVD + tid), g);
+  float g4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 16
+  for (int i = 0; i < kVD; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) g4[u] = fmaf(s_h[i + u], __ldg(gw + (i + u) * kVD + tid), g4[u]);
+  }
+  float g = (g4[0] + g4[1]) + (g4[2] + g4[3]);
   g = fmaf(g, __ldg(g_scale + tid), __ldg(g_shift + tid));
   float y = h * (1.f / (1.f + __expf(-g)));
   if (final_l2norm) {
@@ -275,6 +306,43 @@ netvlad_head_kernel(const float* __restrict__ part_h, int slices, int B, const f
   out[(long long)b * kVD + tid] = y;
 }
 
+struct NvTailArgs {
+  const float* part_v; const float* part_s; int slabs; const float* cw2; float* vlad; float* coln;
+  const float* hw; float* part_h;
+  const float* bn_scale; const float* bn_shift; const float* gw; const float* g_scale; const float* g_shift;
+  int final_l2norm; float* out; int B;
+  unsigned int* barrier;   // zero at launch; the last CTA to leave zeroes it again
+};
+
+__global__ void __launch_bounds__(kVD)
+netvlad_tail_kernel(const NvTailArgs a) {
+  const int G = (int)gridDim.x;
+  for (int w = blockIdx.x; w < a.B * (kVK / kVQ); w += G)
+    nv_finalize_item(w / (kVK / kVQ), w % (kVK / kVQ), a.part_v, a.part_s, a.slabs, a.cw2, a.vlad, a.coln);
+  nv_grid_barrier(a.barrier, (unsigned)G);
+  const int slices = kVD * kVK / kVSlice;
+  const int groups = (a.B + 31) / 32;
+  for (int w = blockIdx.x; w < slices * groups; w += G)
+    nv_project_item(w % slices, (w / slices) * 32, a.vlad, a.hw, a.B, kVD * kVK, a.part_h);
+  nv_grid_barrier(a.barrier, 2u * (unsigned)G);
+  for (int b = blockIdx.x; b < a.B; b += G)
+    nv_head_item(b, a.part_h, slices, a.B, a.coln, a.bn_scale, a.bn_shift, a.gw, a.g_scale, a.g_shift,
+                 a.final_l2norm, a.out);
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(a.barrier, 1u) == 3u * (unsigned)G - 1u) *a.barrier = 0u;
+}
+
+static int netvlad_tail_launch(const NvTailArgs& a, cudaStream_t st) {
+  int dev = 0, sms = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int work = max(a.B * (kVK / kVQ), kVD * kVK / kVSlice);
+  // every CTA resident at once (the barriers spin): two 256-thread CTAs per SM (91 registers, 11 KB each), so that
+  // the projection's 256 weight slices are all in flight together
+  const int grid = work < 2 * sms ? work : 2 * sms;
+  netvlad_tail_kernel<<<grid, kVD, 0, st>>>(a);
+  return launch_status();
+}
+
 static size_t nv_part_v_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVD * kVK * 4, 256); }
 static size_t nv_part_s_bytes(int B) { return align_up((size_t)B * kVMaxSlabs * kVK * 4, 256); }
 static size_t nv_vlad_bytes(int B) { return align_up((size_t)B * kVD * kVK * 4, 256); }
@@ -282,12 +350,13 @@ static size_t nv_coln_bytes(int B) { return align_up((size_t)B * kVK * 4, 256); 
 static size_t nv_part_h_bytes(int B) {
   return align_up((size_t)(kVD * kVK / kVSlice) * B * kVD * 4, 256);
 }
+static size_t nv_barrier_bytes() { return 256; }
 
 // netvlad_tc.cu: the aggregation on the tensor cores (default); DH3D_EXACT_FP32=1 selects the FFMA kernel above
 size_t netvlad_tc_workspace_bytes();
 int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, int N, const float* cw,
                                 const float* bn_scale, const float* bn_shift, float* part_v, float* part_s,
-                                int* P_out, void* ws, cudaStream_t st);
+                                int* P_out, void* ws, unsigned int* zero_word, cudaStream_t st);
 bool exact_fp32();   // capi.cu
 static bool netvlad_use_tc() { return !exact_fp32(); }
 
@@ -295,7 +364,7 @@ size_t netvlad_workspace_bytes(int B, int N, int D, int Kc, int out_dim) {
   (void)N;
   if (B <= 0 || D != kVD || Kc != kVK || out_dim != kVD) return 0;
   return nv_part_v_bytes(B) + nv_part_s_bytes(B) + nv_vlad_bytes(B) + nv_coln_bytes(B) + nv_part_h_bytes(B) +
-         align_up(netvlad_tc_workspace_bytes(), 256);
+         nv_barrier_bytes() + align_up(netvlad_tc_workspace_bytes(), 256);
 }
 
 int netvlad_launch(const float* features, const float* att, int B, int N, int D, int Kc, int out_dim,
@@ -318,21 +387,19 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   float* vlad = reinterpret_cast<float*>(p); p += nv_vlad_bytes(B);
   float* coln = reinterpret_cast<float*>(p); p += nv_coln_bytes(B);
   float* part_h = reinterpret_cast<float*>(p); p += nv_part_h_bytes(B);
+  unsigned int* barrier = reinterpret_cast<unsigned int*>(p); p += nv_barrier_bytes();
   void* tc_ws = p;
+  // (the tail kernel's grid-barrier counter: the workspace is not assumed to be zeroed, the aggregate kernel zeroes it)
+  NvTailArgs tail{part_v, part_s, 0, cw2, vlad, coln, hw, part_h, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
+                  final_l2norm, out, B, barrier};
 
   int rc;
   if (netvlad_use_tc()) {
     int P = 0;
-    rc = netvlad_tc_aggregate_launch(features, att, B, N, cw, cbn_scale, cbn_shift, part_v, part_s, &P, tc_ws, st);
+    rc = netvlad_tc_aggregate_launch(features, att, B, N, cw, cbn_scale, cbn_shift, part_v, part_s, &P, tc_ws, barrier, st);
     if (rc != DH3D_OK) return rc;
-    netvlad_finalize_kernel<<<dim3(B, kVK / kVQ), kVD, 0, st>>>(part_v, part_s, P, cw2, vlad, coln);
-    if ((rc = launch_status()) != DH3D_OK) return rc;
-    const int slices = kVD * kVK / kVSlice;
-    netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
-    if ((rc = launch_status()) != DH3D_OK) return rc;
-    netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, coln, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
-                                          final_l2norm, out);
-    return launch_status();
+    tail.slabs = P;
+    return netvlad_tail_launch(tail, st);
   }
 
   cudaError_t e = cudaFuncSetAttribute(netvlad_aggregate_kernel,
@@ -345,17 +412,11 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   if (slabs > kVMaxSlabs) slabs = kVMaxSlabs;
   while (slabs > 1 && (N + slabs - 1) / slabs < 64) --slabs;
   netvlad_aggregate_kernel<<<dim3(slabs, B), kVD, sizeof(VladSmem), st>>>(
-      features, att, N, slabs, cw, cbn_scale, cbn_shift, part_v, part_s);
+      features, att, N, slabs, cw, cbn_scale, cbn_shift, part_v, part_s, barrier);
   rc = launch_status();
   if (rc != DH3D_OK) return rc;
-  netvlad_finalize_kernel<<<dim3(B, kVK / kVQ), kVD, 0, st>>>(part_v, part_s, slabs, cw2, vlad, coln);
-  if ((rc = launch_status()) != DH3D_OK) return rc;
-  const int slices = kVD * kVK / kVSlice;
-  netvlad_project_kernel<<<dim3(slices, ceil_div(B, 32)), kVD, 0, st>>>(vlad, hw, B, kVD * kVK, part_h);
-  if ((rc = launch_status()) != DH3D_OK) return rc;
-  netvlad_head_kernel<<<B, kVD, 0, st>>>(part_h, slices, B, coln, bn_scale, bn_shift, gw, gbn_scale,
-                                        gbn_shift, final_l2norm, out);
-  return launch_status();
+  tail.slabs = slabs;
+  return netvlad_tail_launch(tail, st);
 }
 
 }  // namespace dh3d

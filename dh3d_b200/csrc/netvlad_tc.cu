@@ -46,6 +46,7 @@ struct NvArgs {
   float* part_v;           // [B][P][256][64]
   float* part_s;           // [B][P][64]
   int N, tiles_per_cta, subslabs, P;
+  unsigned int* zero_word;   // the tail kernel's grid-barrier counter: zeroed here, one launch ahead of its use
 };
 
 // MN-major, 128B-swizzled operand: 128-byte rows of 64 fp16 along M; 8-row K groups 1024 B apart;
@@ -131,6 +132,7 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                    const __grid_constant__ CUtensorMap tmWl, const NvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if (a.zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.zero_word = 0u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NvSmem2::bars);
   uint64_t* raw_full = bars;         // [2] count 1 + tx: a whole raw tile landed in buffer b
   uint64_t* x_full = bars + 2;       // [2] count 128: buffer b converted to xh/xl
@@ -479,7 +481,7 @@ int netvlad_tc_partials(int B, int N, int* ctas_per_cloud, int* tiles_per_cta, i
 // features [B*N, 256] fp32, att [B, N]; writes P partial slabs per cloud into part_v / part_s; returns P in *P_out
 int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, int N, const float* cw,
                                 const float* bn_scale, const float* bn_shift, float* part_v, float* part_s,
-                                int* P_out, void* ws, cudaStream_t st) {
+                                int* P_out, void* ws, unsigned int* zero_word, cudaStream_t st) {
   int C, tpc, nf;
   const int P = netvlad_tc_partials(B, N, &C, &tpc, &nf);
   if (P > 32) return DH3D_ERR_UNSUPPORTED;
@@ -491,7 +493,7 @@ int netvlad_tc_aggregate_launch(const float* features, const float* att, int B, 
   if ((rc = make_map(&mx, features, (long long)B * N, kND, kND, kNT)) != DH3D_OK) return rc;
   if ((rc = nv_make_map_f16(&mh, base, kNK, kND, kND, kNK)) != DH3D_OK) return rc;
   if ((rc = nv_make_map_f16(&ml, base + plane, kNK, kND, kND, kNK)) != DH3D_OK) return rc;
-  NvArgs a{att, reinterpret_cast<const float*>(base + 2 * plane), bn_scale, bn_shift, part_v, part_s, N, tpc, nf, P};
+  NvArgs a{att, reinterpret_cast<const float*>(base + 2 * plane), bn_scale, bn_shift, part_v, part_s, N, tpc, nf, P, zero_word};
   const int smem = (int)NvSmem2::total + 1024;
   cudaError_t e = cudaFuncSetAttribute(netvlad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return (int)e;

@@ -44,19 +44,23 @@ constexpr uint32_t kCAStageBytes = 128 * 128;   // 128 rows x 32 channels fp32
 // static point per group (see the consumer branch).
 template <int BN, bool K8>
 struct CACfg {
-  static constexpr int kStages = 2;                           // UMMA operand stages
-  // gather stages (16 KB each).  K == 8 path: 6 where the operand stages leave room (BN = 64: the 32->64 and 64->64
-  // layers, 85 % of DH3D's gathered bytes) = 5 rows x 32 B in flight per consumer thread, 80 KB per SM; 4 at BN = 128.
-  static constexpr int kGStages = K8 ? (BN <= 64 ? 6 : 4) : (BN <= 64 ? 5 : 3);
+  static constexpr int kStages = 2;                           // UMMA A-operand stages (moment slabs, hi + lo)
+  // Theta tiles have their OWN ring, decoupled from the A stages: with the tiles inside the A stages (r1) the TMA of
+  // slab i + 2 could only be issued once the MMAs of slab i had completed, so every slab paid an L2 round trip
+  static constexpr int kBStages = K8 ? (BN <= 64 ? 4 : 2) : 2;
+  // gather stages (16 KB each): ring depth 6 / 3 / 2 measured within 10 % of each other (profiles/flexconv_*_r2s.txt)
+  static constexpr int kGStages = K8 ? 4 : (BN <= 64 ? 5 : 3);
   static constexpr int kOutRows = K8 ? 16 : 32;  // rows per epilogue TMA store (smem budget)
   static constexpr uint32_t kOutBytes = 4 * kOutRows * 32 * 4;
   static constexpr uint32_t kBBytes = BN * kTcBK * 4;
-  static constexpr uint32_t kStageBytes = 2 * kTcABytes + 2 * kBBytes;
+  static constexpr uint32_t kStageBytes = 2 * kTcABytes;
+  static constexpr uint32_t kBStageBytes = 2 * kBBytes;
   static constexpr uint32_t kDeltaBytes = 128 * kCAKB * 16;   // float4 per (row, slot)
   static constexpr uint32_t kIdxBytes = 128 * kCAKB * 4;      // global feature row per (row, slot)
   static constexpr uint32_t kParamBytes = 2 * 2 * BN * 4;     // double-buffered scale/shift slices
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kGStages * kCAStageBytes + kDeltaBytes +
-                                         kIdxBytes + kOutBytes + kParamBytes + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBStages * kBStageBytes + kGStages * kCAStageBytes +
+                                         kDeltaBytes + kIdxBytes + kOutBytes + kParamBytes + 256 /*barriers*/ +
+                                         1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
@@ -68,19 +72,22 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
                    const CAArgs a) {
   using Cfg = CACfg<BN, K8>;
   constexpr int S = Cfg::kStages;
+  constexpr int SB = Cfg::kBStages;
   constexpr int G = Cfg::kGStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* gbase = smem + S * Cfg::kStageBytes;                            // gather stages, 1024-aligned
+  uint8_t* bring = smem + S * Cfg::kStageBytes;                            // Theta ring, 1024-aligned
+  uint8_t* gbase = bring + SB * Cfg::kBStageBytes;                         // gather stages, 1024-aligned
   float4* sdelta = reinterpret_cast<float4*>(gbase + G * kCAStageBytes);   // [128][kCAKB]
   int* sidx = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sdelta) + Cfg::kDeltaBytes);  // [128][kCAKB]
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(sidx) + Cfg::kIdxBytes;
   float* params = reinterpret_cast<float*>(out_stage + Cfg::kOutBytes);  // [2][2][BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(params) + Cfg::kParamBytes);
-  uint64_t* bfull = bars;               // [S] Theta tiles landed          (count 1 + tx)
-  uint64_t* afull = bars + S;           // [S] A hi/lo slab written        (count 16, one per consumer warp)
-  uint64_t* empty = bars + 2 * S;       // [S] MMAs reading the stage done (count 1, tcgen05.commit)
-  uint64_t* tmem_full = bars + 3 * S;
+  uint64_t* afull = bars;               // [S]  A hi/lo slab written         (count 16, one per consumer warp)
+  uint64_t* empty = bars + S;           // [S]  MMAs reading the A stage done (count 1, tcgen05.commit)
+  uint64_t* bfull = bars + 2 * S;       // [SB] Theta tiles landed            (count 1 + tx)
+  uint64_t* bempty = bars + 2 * S + SB; // [SB] MMAs reading the tiles done   (count 1, tcgen05.commit)
+  uint64_t* tmem_full = bars + 2 * S + 2 * SB;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -93,14 +100,17 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
 
   auto stage_a = [&](int s) { return smem + s * Cfg::kStageBytes; };
   auto stage_alo = [&](int s) { return smem + s * Cfg::kStageBytes + kTcABytes; };
-  auto stage_bhi = [&](int s) { return smem + s * Cfg::kStageBytes + 2 * kTcABytes; };
-  auto stage_blo = [&](int s) { return smem + s * Cfg::kStageBytes + 2 * kTcABytes + Cfg::kBBytes; };
+  auto stage_bhi = [&](int s) { return bring + s * Cfg::kBStageBytes; };
+  auto stage_blo = [&](int s) { return bring + s * Cfg::kBStageBytes + Cfg::kBBytes; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&bfull[s], 1);
       mbar_init(&afull[s], kCAConsumerWarps);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -128,9 +138,9 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
         for (int nt = 0; nt < num_nt; ++nt)
           for (int cg = 0; cg < num_cg; ++cg)
             for (int p = 0; p < 4; ++p, ++it) {
-              const int s = it % S;
-              const uint32_t ph = (it / S) & 1;
-              mbar_wait(&empty[s], ph ^ 1);
+              const int s = it % SB;
+              const uint32_t ph = (it / SB) & 1;
+              mbar_wait(&bempty[s], ph ^ 1);
               mbar_arrive_expect_tx(&bfull[s], 2 * Cfg::kBBytes);
               const int k0 = p * a.Din + cg * kTcBK;  // row block of Theta_ext == column block of Theta_ext^T
               tma_load_2d(stage_bhi(s), &tmBhi, k0, nt * BN, &bfull[s]);
@@ -150,15 +160,14 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t tmem_d = tmem_base + acc * BN;
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
-            const int s = it % S;
-            const uint32_t ph = (it / S) & 1;
-            mbar_wait(&bfull[s], ph);
-            mbar_wait(&afull[s], ph);
+            const int s = it % S, sb = it % SB;
+            mbar_wait(&bfull[sb], (it / SB) & 1);
+            mbar_wait(&afull[s], (it / S) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_hi = umma_desc_sw128(smem_u32(stage_a(s)));
             const uint64_t a_lo = umma_desc_sw128(smem_u32(stage_alo(s)));
-            const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_bhi(s)));
-            const uint64_t b_lo = umma_desc_sw128(smem_u32(stage_blo(s)));
+            const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_bhi(sb)));
+            const uint64_t b_lo = umma_desc_sw128(smem_u32(stage_blo(sb)));
 #pragma unroll
             for (int k = 0; k < kTcBK / 8; ++k) {
               const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;
@@ -167,6 +176,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
               umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
             }
             umma_commit(&empty[s]);
+            umma_commit(&bempty[sb]);
           }
           umma_commit(&tmem_full[acc]);
         }

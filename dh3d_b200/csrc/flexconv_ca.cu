@@ -42,8 +42,9 @@ constexpr uint32_t kCAStageBytes = 128 * 128;   // 128 rows x 32 channels fp32
 // K8 = the K == 8 fast path (every FlexConv of DH3D): the neighbour loop is fully unrolled, so the ring slot, the
 // table slot and the operand stage of every item are compile-time constants and the issue cursor advances at one
 // static point per group (see the consumer branch).
-template <int BN, bool K8>
+template <int BN, int NB>   // NB = K / 8 for the unrolled 8-slot schedule (K = 8, 16, 32), 0 = generic loop (any K)
 struct CACfg {
+  static constexpr bool K8 = NB > 0;
   static constexpr int kStages = 2;                           // UMMA A-operand stages (moment slabs, hi + lo)
   // Theta tiles have their OWN ring, decoupled from the A stages: with the tiles inside the A stages (r1) the TMA of
   // slab i + 2 could only be issued once the MMAs of slab i had completed, so every slab paid an L2 round trip
@@ -65,12 +66,13 @@ struct CACfg {
   static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
-template <int BN, bool K8>
+template <int BN, int NB>
 __global__ void __launch_bounds__(kCAThreads, 1)
 flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY,
                    const CAArgs a) {
-  using Cfg = CACfg<BN, K8>;
+  using Cfg = CACfg<BN, NB>;
+  constexpr bool K8 = NB > 0;
   constexpr int S = Cfg::kStages;
   constexpr int SB = Cfg::kBStages;
   constexpr int G = Cfg::kGStages;
@@ -202,13 +204,14 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
 
     // ---- issue side: tile i_mt, group (i_nt, i_cg); entering a tile fills the index table of this warp's rows
     // and starts the loads the offset table of that tile will need three items later
-    int i_mt = blockIdx.x, i_cg = 0, i_g = 0;
+    int i_mt = blockIdx.x, i_cg = 0, i_g = 0, i_b = 0;
+    constexpr int nbatch = NB > 0 ? NB : 1;   // K == 8: one batch, the tables of a tile serve all its groups
     float nx[6], pc[3];
-    auto enter_tile = [&](int mt) {
+    auto enter_batch = [&](int mt, int b) {
       const int row = mt * kTcBM + r;
       const int rr = row < a.rows ? row : 0;   // tail rows gather row 0 (their outputs are clipped)
       const int cloud0 = (rr / a.n_per_cloud) * a.n_per_cloud;
-      const int2 nb = __ldg(reinterpret_cast<const int2*>(a.nbr + (long long)rr * 8 + 2 * seg));
+      const int2 nb = __ldg(reinterpret_cast<const int2*>(a.nbr + (long long)rr * a.K + 8 * b + 2 * seg));
       const int v0 = cloud0 + nb.x, v1 = cloud0 + nb.y;
       __syncwarp();
       irow[(2 * seg) ^ rw] = v0;
@@ -233,50 +236,61 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
       i_off += kCAStageBytes;
       if (i_off == kRing) i_off = 0;
     };
-    auto next_group = [&]() {
-      if (++i_cg == num_cg) i_cg = 0;
-      if (++i_g == groups) {
-        i_g = 0;
-        i_mt += gridDim.x;
-        if (i_mt < num_mt) enter_tile(i_mt);
+    // the issue cursor crosses a batch boundary: next batch of the group, else next group / tile; K > 8 refills the
+    // tables at every batch (loaded AH items before the consume side needs them), K == 8 once per tile
+    auto next_batch = [&]() {
+      bool new_tile = false;
+      if (++i_b == nbatch) {
+        i_b = 0;
+        if (++i_cg == num_cg) i_cg = 0;
+        if (++i_g == groups) {
+          i_g = 0;
+          i_mt += gridDim.x;
+          new_tile = true;
+        }
       }
+      if (i_mt < num_mt && (nbatch > 1 || new_tile)) enter_batch(i_mt, i_b);
     };
-    if (i_mt < num_mt) enter_tile(i_mt);
+    if (i_mt < num_mt) enter_batch(i_mt, 0);
 #pragma unroll
     for (int i = 0; i < AH; ++i) issue(i);
 
     // ---- consume side
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
-      // offset table of this tile from the coordinates loaded when the issue side entered it
-      __syncwarp();
-      drow[(2 * seg) ^ rw] = make_float4(nx[0] - pc[0], nx[1] - pc[1], nx[2] - pc[2], 0.f);
-      drow[(2 * seg + 1) ^ rw] = make_float4(nx[3] - pc[0], nx[4] - pc[1], nx[5] - pc[2], 0.f);
-      __syncwarp();
       for (int g = 0; g < groups; ++g) {
         unsigned long long m[4][4];  // [moment p'][channel pair]
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
           for (int c = 0; c < 4; ++c) m[p][c] = 0ull;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(AH - 1) : "memory");  // this thread's item k landed
-          const uint8_t* gs = gbase + c_off;
-          c_off += kCAStageBytes;
-          if (c_off == kRing) c_off = 0;
-          const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(gs + o0);
-          const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(gs + o1);
-          const float4 d = drow[k ^ rw];
-          const unsigned long long fv[4] = {f0.x, f0.y, f1.x, f1.y};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            fadd2(m[0][c], fv[c]);
-            ffma2(m[1][c], fv[c], d.x);
-            ffma2(m[2][c], fv[c], d.y);
-            ffma2(m[3][c], fv[c], d.z);
+        for (int b = 0; b < nbatch; ++b) {
+          if (nbatch > 1 || g == 0) {
+            // offset table of this batch from the coordinates loaded when the issue side entered it
+            __syncwarp();
+            drow[(2 * seg) ^ rw] = make_float4(nx[0] - pc[0], nx[1] - pc[1], nx[2] - pc[2], 0.f);
+            drow[(2 * seg + 1) ^ rw] = make_float4(nx[3] - pc[0], nx[4] - pc[1], nx[5] - pc[2], 0.f);
+            __syncwarp();
           }
-          if (k == 8 - AH) next_group();
-          issue((k + AH) & 7);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(AH - 1) : "memory");  // this thread's item k landed
+            const uint8_t* gs = gbase + c_off;
+            c_off += kCAStageBytes;
+            if (c_off == kRing) c_off = 0;
+            const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(gs + o0);
+            const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(gs + o1);
+            const float4 d = drow[k ^ rw];
+            const unsigned long long fv[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              fadd2(m[0][c], fv[c]);
+              ffma2(m[1][c], fv[c], d.x);
+              ffma2(m[2][c], fv[c], d.y);
+              ffma2(m[3][c], fv[c], d.z);
+            }
+            if (k == 8 - AH) next_batch();
+            issue((k + AH) & 7);
+          }
         }
         // 4 K-slabs (p' = 1, x, y, z) -> operand stages p' & 1, swizzled K-major, hi (raw) + lo
 #pragma unroll
@@ -506,16 +520,16 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
   }
 }
 
-template <int BN, bool K8>
+template <int BN, int NB>
 static int launch_ca(const CAArgs& a, const float* thi, const float* tlo, float* out, cudaStream_t st) {
-  using Cfg = CACfg<BN, K8>;
+  using Cfg = CACfg<BN, NB>;
   CUtensorMap mh, ml, my;
   int rc;
   const int Kd = 4 * a.Din;
   if ((rc = make_map(&mh, thi, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
   if ((rc = make_map(&ml, tlo, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
   if ((rc = make_map(&my, out, a.rows, a.Dout, a.Dout, Cfg::kOutRows)) != DH3D_OK) return rc;
-  auto kern = flexconv_ca_kernel<BN, K8>;
+  auto kern = flexconv_ca_kernel<BN, NB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
@@ -534,12 +548,13 @@ int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, 
   const float* thi = reinterpret_cast<const float*>(theta_packed);
   const float* tlo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(theta_packed) +
                                                     align_up((size_t)4 * Din * Dout * sizeof(float), 256));
-  if (K == 8 && ((uintptr_t)nbr & 7) == 0) {
-    if (Dout <= 64) return launch_ca<64, true>(a, thi, tlo, out, st);
-    return launch_ca<128, true>(a, thi, tlo, out, st);
+  if (((uintptr_t)nbr & 7) == 0) {   // unrolled 8-slot schedule, K / 8 batches per group
+    if (K == 8) return Dout <= 64 ? launch_ca<64, 1>(a, thi, tlo, out, st) : launch_ca<128, 1>(a, thi, tlo, out, st);
+    if (K == 16) return Dout <= 64 ? launch_ca<64, 2>(a, thi, tlo, out, st) : launch_ca<128, 2>(a, thi, tlo, out, st);
+    if (K == 32) return Dout <= 64 ? launch_ca<64, 4>(a, thi, tlo, out, st) : launch_ca<128, 4>(a, thi, tlo, out, st);
   }
-  if (Dout <= 64) return launch_ca<64, false>(a, thi, tlo, out, st);
-  return launch_ca<128, false>(a, thi, tlo, out, st);
+  if (Dout <= 64) return launch_ca<64, 0>(a, thi, tlo, out, st);
+  return launch_ca<128, 0>(a, thi, tlo, out, st);
 }
 
 }  // namespace dh3d

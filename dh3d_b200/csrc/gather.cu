@@ -406,7 +406,7 @@ three_interp_warp_kernel(const float* __restrict__ points, const int32_t* __rest
       w = __fdiv_rn(v, __fadd_rn(__fadd_rn(v1, v2), v3));
     }
     const int nr = (int)(rows - r0 < 8 ? rows - r0 : 8);
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < nr; ++j) {
       const float w1 = __shfl_sync(0xffffffffu, w, 3 * j), w2 = __shfl_sync(0xffffffffu, w, 3 * j + 1),
                   w3 = __shfl_sync(0xffffffffu, w, 3 * j + 2);
@@ -421,7 +421,7 @@ three_interp_warp_kernel(const float* __restrict__ points, const int32_t* __rest
         v.y = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(bb.y, w2)), __fmul_rn(cc.y, w3));
         v.z = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(bb.z, w2)), __fmul_rn(cc.z, w3));
         v.w = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(bb.w, w2)), __fmul_rn(cc.w, w3));
-        *reinterpret_cast<float4*>(o + col) = v;
+        __stcs(reinterpret_cast<float4*>(o + col), v);   // written once, read by the next kernel from HBM anyway
       }
     }
   }

@@ -21,13 +21,16 @@
 // Persistent warp-specialised structure (320 threads, one CTA per SM).  With enough M tiles the CTAs run as PAIRS
 // (MC = 2, one thread-block cluster per TPC) issuing tcgen05.mma.cta_group::2: the pair's accumulator is 256 rows x BN
 // (each CTA's 128 rows in its own TMEM), each CTA stages its own X tile and only its N HALF of the W tile, and the
-// leader CTA's MMA thread issues for both.  A single-CTA 128 x 256 x 16 MMA reads 4 KB of A + 8 KB of B from shared
-// memory per 128 tensor cycles = 96 of the SM's 128 B/clk, and with the TMA writes and the split warps' traffic on
-// top the 256 -> 1024 heads were SHARED-MEMORY-bandwidth bound at 66 % tensor-pipe activity (ncu r1s/r2j: 152 KB of
-// shared-memory traffic per K slab vs 768 MMA cycles); the pair form reads 4 + 4 KB per MMA and stages half the W
-// bytes per CTA (112 KB per slab).  Structure:
+// leader CTA's MMA thread issues for both; split / epilogue warps of the peer arrive on the leader's barriers, the
+// leader's tcgen05.commit is multicast to both CTAs.  Why pairs: each CTA stages half the W bytes, which buys a 6-deep
+// stage ring in the same shared memory, and the MMA reads 4 + 4 KB per CTA instead of 4 + 8.  (tcgen05.mma itself issues
+// every 128 cycles in either form and under any shared-memory load -- scripts/ubench/mma_rate.cu; what held the
+// single-CTA kernel at 66 % tensor-pipe activity on the 256 -> 1024 heads was the split warps, busy 100 % of the time
+// re-converting X for every N pass: wide layers with K <= 256 therefore run gemm_head16.cu, which keeps the converted
+// tile resident.)  Structure:
 //   * K slabs of 32: raw X tile [128 x 32] fp32 (TMA, 128B swizzle) -> warps 2-5 write xh / xl as
-//     [128 x 32] fp16 tiles in the 64B-swizzled K-major layout (conflict-free 16-byte loads/stores);
+//     [128 x 32] fp16 tiles in the 64B-swizzled K-major layout IN PLACE over the raw slab (every split thread holds
+//     its part of the slab in registers before any of them writes: one named barrier per slab);
 //     W_h^T / W_l^T tiles [BN x 32] fp16 arrive by TMA in that layout (pre-split once per weight);
 //   * BN up to 256 (two 256-column TMEM accumulators = all 512 columns), which halves how often
 //     the X tile is re-streamed and re-split for wide layers (256 -> 1024 heads: 4 N tiles);

@@ -85,11 +85,18 @@ def test_tensor_core_kernels_are_tcgen05_tma_code():
         assert _count(ops, "UTMALDG") >= 3, name          # TMA loads of the X / W tiles
         assert _count(ops, "LDTM") >= 1, name             # tcgen05.ld of the accumulator
     assert _count(gemm[_pick(gemm, "gemm_join16_kernel")[0]], "UTMASTG") >= 1     # TMA stores of y / its normalised copy
+    head = _functions("gemm_head16.o")
+    ops = head[_pick(head, "gemm_head16_kernel")[0]]      # resident-activation head kernel, CTA pairs
+    assert _count(ops, "UTCHMMA.2CTA") >= 6 and _count(ops, "UTMALDG") >= 3 and _count(ops, "LDTM") >= 1
+    assert _count(ops, "UTMASTG") == 0                    # the [M, 1024] hidden layer never leaves the SM
+    pair = gemm[_pick(gemm, "gemm_tc16_kernelILi256ELb1ELi2E")[0]]
+    assert _count(pair, "UTCHMMA.2CTA") >= 6              # tcgen05.mma.cta_group::2
     flex = _functions("flexconv_ca.o")
-    for name in _pick(flex, "flexconv_ca_kernelILi64ELb1E") + _pick(flex, "flexconv_ca_kernelILi128ELb1E"):
-        ops = flex[name]
-        assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "LDGSTS") >= 16 and _count(ops, "UTMASTG") >= 1, name
-        assert _count(ops, "FFMA2") >= 8 * 12 and _count(ops, "FADD2") >= 8 * 4, name       # 8 unrolled neighbour slots
+    for nb in (1, 2, 4):                                  # K = 8 (DH3D), 16, 32: the unrolled 8-slot schedule
+        for name in (_pick(flex, "flexconv_ca_kernelILi64ELi%dE" % nb) + _pick(flex, "flexconv_ca_kernelILi128ELi%dE" % nb)):
+            ops = flex[name]
+            assert _count(ops, "UTCHMMA") >= 12 and _count(ops, "LDGSTS") >= 16 and _count(ops, "UTMASTG") >= 1, name
+            assert _count(ops, "FFMA2") >= 8 * 12 and _count(ops, "FADD2") >= 8 * 4, name   # 8 unrolled neighbour slots
     nv = _functions("netvlad_tc.o")
     ops = nv[_pick(nv, "netvlad_tc2_kernel")[0]]
     assert _count(ops, "UTCHMMA") >= 72 and _count(ops, "UTMALDG") >= 8 and _count(ops, "LDTM") >= 2
@@ -98,7 +105,7 @@ def test_tensor_core_kernels_are_tcgen05_tma_code():
 def test_no_kernel_spills_to_local_memory_heavily():
     """Register budgets are part of the design (80 registers at 704 threads, 168 at 320): a change that pushes a
     hot loop into local memory shows up here as a jump in LDL/STL counts."""
-    budgets = {("flexconv_ca.o", "flexconv_ca_kernelILi64ELb1E"): 40, ("gemm_tc16.o", "gemm_join16_kernel"): 4,
+    budgets = {("flexconv_ca.o", "flexconv_ca_kernelILi64ELi1E"): 40, ("gemm_head16.o", "gemm_head16_kernel"): 0, ("gemm_tc16.o", "gemm_join16_kernel"): 4,
                ("se_fused.o", "se_pool_excite_kernelILi64E"): 0, ("knn.o", "knn_query_kernelILi8ELb1ELb1E"): 8,
                ("netvlad_tc.o", "netvlad_tc2_kernel"): 24}
     for (obj, needle), limit in budgets.items():

@@ -393,22 +393,20 @@ struct ThreeNnMetric {  // tf_interpolate.cpp:60-103: un-fused (dx*dx + dy*dy) +
   static constexpr int kInitRank = 0;
 };
 
-constexpr int kKnnCap = 16;  // buffered candidates per query before a flush
 
 // One thread per query, KC-entry sorted list of packed (key bits, rank) pairs in registers.  A non-negative
 // float orders like its bit pattern, so one 64-bit integer compare is the reference's (key, tie-rank) order.
-// The scan loop never branches into the insertion: a candidate under the lane's bound is appended to the
-// lane's column of a shared-memory buffer (predicated store); the warp inserts the buffered candidates
-// together when some lane's column fills up (or at the end of a chunk), which is where the bound tightens.
-// A stale bound is only looser, so nothing is lost.  KC >= K; EXACT: K == KC and 16-byte aligned outputs.
+// The scan loop never branches into the insertion: it only sets one bit per candidate that is under the lane's
+// bound; at the end of the chunk the warp inserts the marked candidates together (coordinates read back from the
+// staged chunk, distance recomputed with the same IEEE operations), which is where the bound tightens.  A stale
+// bound is only looser, so nothing is lost.  KC >= K; EXACT: K == KC and 16-byte aligned outputs.
 // SELF: queries are the candidates themselves (k-NN; the walk starts at the warp's own chunk), otherwise
 // the walk starts at the chunk whose box is nearest to the warp's first query (3-NN).
 template <int KC, bool EXACT, bool SELF, class M>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const float4* __restrict__ sorted,
-                 const float4* __restrict__ boxes, int Np, int T, int logT, int logV, int K, int flush_min,
+                 const float4* __restrict__ boxes, int Np, int T, int logT, int logV, int K,
                  int32_t* __restrict__ ids, float* __restrict__ dists) {
-  __shared__ float2 s_buf[kKnnCap][kKnnThreads];
   __shared__ __align__(16) float4 s_chunk[kKnnThreads / 32][kKnnChunk];
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -434,26 +432,28 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   for (int j = 0; j < KC; ++j) L[j] = kInit;
   float thr2 = active ? CUDART_INF_F : -1.f;  // inactive lanes never pass
   unsigned long long kth_pk = kInit;           // the lane's current K-th packed (key, rank)
-  int cnt = 0;
 
-  auto flush = [&]() {
-    int m = cnt;
+  // Inserts the candidates of the staged chunk whose bit is set in `mask` (the scan's "under the lane's bound" bits)
+  // into the lane's list.  The candidate's coordinates are read back from the warp's staged chunk (pair-interleaved
+  // floats: candidate j = 2P + h has x, y at floats 8P + h, 8P + 2 + h, z and its index at 8P + 4 + h, 8P + 6 + h) and
+  // its distance recomputed with the scalar form of the metric (the same IEEE operations as the packed scan).
+  auto flush = [&](uint32_t mask, const float* cf) {
+    int m = __popc(mask);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     for (int e = 0; e < m; ++e) {
-      if (e < cnt) {
-        const float2 c = s_buf[e][tid];
-        const int x = __float_as_int(c.y);
-        if (x >= 0) {
-          const unsigned long long pk = ((unsigned long long)__float_as_uint(M::key(c.x)) << 32) |
+      if (mask != 0u) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const float* c = cf + 8 * (j >> 1) + (j & 1);
+        const int x = __float_as_int(c[6]);
+        const float d2 = M::d2(c[0] - qx, c[2] - qy, c[4] - qz);
+        // re-test against the bound as tightened by this flush's own insertions: most marked candidates of a chunk
+        // fall out here, before the sqrt / pack / 64-bit insertion network
+        if (x >= 0 && d2 <= thr2) {
+          const unsigned long long pk = ((unsigned long long)__float_as_uint(M::key(d2)) << 32) |
                                         (uint32_t)M::rank_of(x, T, logT, logV);
-          unsigned long long kth = L[KC - 1];
-          if constexpr (!EXACT) {
-            kth = L[0];
-#pragma unroll
-            for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
-          }
-          if (pk < kth) {
+          if (pk < kth_pk) {
 #pragma unroll
             for (int i = KC - 1; i > 0; --i) {
               const bool before_prev = pk < L[i - 1];
@@ -461,19 +461,18 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
               L[i] = before_prev ? L[i - 1] : (before_here ? pk : L[i]);
             }
             if (pk < L[0]) L[0] = pk;
+            unsigned long long kth = L[KC - 1];
+            if constexpr (!EXACT) {
+              kth = L[0];
+#pragma unroll
+              for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
+            }
+            kth_pk = kth;
+            thr2 = M::bound(__uint_as_float((uint32_t)(kth >> 32)));
           }
         }
       }
     }
-    cnt = 0;
-    unsigned long long kth = L[KC - 1];
-    if constexpr (!EXACT) {
-      kth = L[0];
-#pragma unroll
-      for (int i = 1; i < KC; ++i) kth = (i < K) ? L[i] : kth;
-    }
-    kth_pk = kth;
-    if (active) thr2 = M::bound(__uint_as_float((uint32_t)(kth >> 32)));
   };
 
   // Can a box still hold a candidate that enters this lane's list?  lb = lower bound of every d2 in the box
@@ -584,35 +583,27 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
       s_chunk[tid >> 5][lane] = odd ? make_float4(s0v, mine.z, s1v, mine.w) : make_float4(mine.x, s0v, mine.y, s1v);
       __syncwarp();
       const ulonglong2* cand = reinterpret_cast<const ulonglong2*>(s_chunk[tid >> 5]);
+      // The scan only records WHICH candidates are under the lane's bound, one bit each: 12 instructions per candidate
+      // pair (2 LDS.128, 6 packed FP, 2 FSETP, 2 predicated LOP3) with no dependent address arithmetic; the buffered
+      // (d2, index) append it replaces cost 21 (predicated STS.64 + counter + address chain per candidate).
+      uint32_t mask = 0u;
 #pragma unroll
-      for (int j0 = 0; j0 < kKnnChunk; j0 += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const ulonglong2 xy = cand[j0 + u], zw = cand[j0 + u + 1];
-          float2 d2;
-          if constexpr (M::kPacked) {
-            d2 = unpack2(M::d2v(fsub2s(xy.x, qx), fsub2s(xy.y, qy), fsub2s(zw.x, qz)));
-          } else {
-            const float2 x = unpack2(xy.x), yv = unpack2(xy.y), z = unpack2(zw.x);
-            d2.x = M::d2(x.x - qx, yv.x - qy, z.x - qz);
-            d2.y = M::d2(x.y - qx, yv.y - qy, z.y - qz);
-          }
-          const float2 w = unpack2(zw.y);
-          if (d2.x <= thr2) {
-            s_buf[cnt][tid] = make_float2(d2.x, w.x);
-            ++cnt;
-          }
-          if (d2.y <= thr2) {
-            s_buf[cnt][tid] = make_float2(d2.y, w.y);
-            ++cnt;
-          }
+      for (int j0 = 0; j0 < kKnnChunk; j0 += 2) {
+        const ulonglong2 xy = cand[j0], zw = cand[j0 + 1];
+        float2 d2;
+        if constexpr (M::kPacked) {
+          d2 = unpack2(M::d2v(fsub2s(xy.x, qx), fsub2s(xy.y, qy), fsub2s(zw.x, qz)));
+        } else {
+          const float2 x = unpack2(xy.x), yv = unpack2(xy.y), z = unpack2(zw.x);
+          d2.x = M::d2(x.x - qx, yv.x - qy, z.x - qz);
+          d2.y = M::d2(x.y - qx, yv.y - qy, z.y - qz);
         }
-        if (__any_sync(0xffffffffu, cnt > kKnnCap - 8)) flush();
+        if (d2.x <= thr2) mask |= 1u << j0;
+        if (d2.y <= thr2) mask |= 2u << j0;
       }
-      if (__any_sync(0xffffffffu, cnt >= flush_min)) flush();
+      if (__any_sync(0xffffffffu, mask != 0u)) flush(mask, reinterpret_cast<const float*>(s_chunk[tid >> 5]));
     }
   }
-  flush();
 
   if (active) {
     int32_t* oi = ids + ((long long)b * Nq + y) * K;
@@ -639,8 +630,6 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   }
 }
 
-static int knn_flush_min() { return 1; }   // flush the candidate buffer at the end of every chunk
-
 int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
                float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (!pos || !ids || !dists) return DH3D_ERR_NULL;
@@ -657,10 +646,9 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(Np, kKnnThreads), B);
   const bool vec_ok = (((uintptr_t)ids | (uintptr_t)dists) & 15) == 0;
-  const int fm = knn_flush_min();
 #define DH3D_KNN(KC, EX)                                                                              \
   knn_query_kernel<KC, EX, true, KnnMetric><<<grid, kKnnThreads, 0, st>>>(sorted, N, Np, sorted, boxes, Np, \
-                                                                          o.T, o.logT, o.logV, K, fm, ids,   \
+                                                                          o.T, o.logT, o.logV, K, ids,       \
                                                                           dists)
   if (K == 8 && vec_ok) DH3D_KNN(8, true);
   else if (K == 16 && vec_ok) DH3D_KNN(16, true);
@@ -707,7 +695,7 @@ int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* 
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(np1, kKnnThreads), b);
   knn_query_kernel<4, false, false, ThreeNnMetric><<<grid, kKnnThreads, 0, st>>>(
-      queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, knn_flush_min(), idx, dist);
+      queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, idx, dist);
   return launch_status();
 }
 

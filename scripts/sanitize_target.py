@@ -1,8 +1,8 @@
 """One small launch of every hand-synchronised kernel (compute-sanitizer target):
     compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python scripts/sanitize_target.py [names...]
 fps (DSMEM spin protocol, 4-CTA clusters), flexconv (cp.async ring + mbarrier stages + tcgen05), netvlad (TMA ring,
-in-place split, TMEM hand-offs), gemm heads / join (TMA multicast clusters, out-of-window row queue), knn / three_nn
-(shared-memory candidate buffers, warp-synchronous flushes), se_pool_excite, gather family."""
+in-place split, TMEM hand-offs, grid-barrier tail), gemm heads / join (CTA pairs with remote mbarrier arrives, in-place
+split, resident-activation head, out-of-window row queue), knn / three_nn (staged chunks, warp-synchronous flushes), se_pool_excite, gather family."""
 import sys
 
 import torch
@@ -44,6 +44,10 @@ if want("flexconv"):
         ops.flex_conv(rnd(2, 2048, ci), rnd(3, ci, co) / 8, rnd(ci, co) / 8, nbr, pts)
     nbr16, _ = ops.knn_points(pts, 16)
     ops.flex_conv(rnd(2, 2048, 128), rnd(3, 128, 128) / 8, rnd(128, 128) / 8, nbr16, pts)
+    nbr32, _ = ops.knn_points(pts, 32)
+    ops.flex_conv(rnd(2, 2048, 128), rnd(3, 128, 128) / 8, rnd(128, 128) / 8, nbr32, pts)   # K = 32: four batches per group
+    nbr12, _ = ops.knn_points(pts, 12)
+    ops.flex_conv(rnd(2, 2048, 64), rnd(3, 64, 64) / 8, rnd(64, 64) / 8, nbr12, pts)        # generic loop (K % 8 != 0)
     ops.flex_conv(rnd(2, 2048, 8), rnd(3, 8, 12) / 8, rnd(8, 12) / 8, nbr, pts)
     print("flexconv ok")
 if want("gather"):
@@ -53,12 +57,13 @@ if want("gather"):
     ops.se_pool_excite(f, nbr, rnd(64, 16) / 8, rnd(16), rnd(16, 64) / 4, rnd(64))
     print("gather ok")
 if want("gemm"):
-    x = rnd(3000, 256)
+    x = rnd(4200, 256)    # 33 row tiles: CTA pairs (tcgen05.mma.cta_group::2) and the resident-activation head kernel
     x[17] *= 1e6          # one out-of-window row: exercises the queue + fp32 recompute
     w = rnd(256, 1024) / 16
     p = ops.linear_prepack(w)
     ops.linear(x, w, packed=p, act=1)
     ops.linear_rowdot(x, p, None, None, 1, rnd(1024) / 32, 0.1, 2)
+    ops.linear_rowdot(x[:3000].contiguous(), p, None, None, 1, rnd(1024) / 32, 0.1, 2)   # single-CTA streaming kernel
     xa, xb = rnd(3000, 192), rnd(3000, 64)
     xa[5] *= 1e5
     ops.linear_join(xa, ops.linear_prepack(rnd(192, 128) / 14), None, None, 1, xb, ops.linear_prepack(rnd(64, 128) / 8),

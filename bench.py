@@ -180,6 +180,9 @@ def algorithmic(tag, name):
     if name in ("dh3d_flex_conv_pm", "dh3d_flex_conv_pm_packed"):
         n, K, Ci, Co = d["n"], d["K"], d["Ci"], d["Co"]
         return 4.0 * (n * Ci + n * Co + n * K + 3 * n + 4 * Ci * Co), 8.0 * n * K * Ci + 8.0 * n * Ci * Co, "hbm"
+    if name == "dh3d_linear_chain_packed":  # x and both weights once, y once; the hidden [M,H] activation stays on the SM
+        M, K, H, N = d["M"], d["K"], d["H"], d["N"]
+        return 4.0 * (M * K + K * H + H * N + M * N), 2.0 * M * (K * H + H * N), "hbm"
     if name == "dh3d_linear_join_packed":   # both inputs and weights once, y and its normalised copy once
         M, Ka, Kb, N = d["M"], d["Ka"], d["Kb"], d["N"]
         return 4.0 * (M * (Ka + Kb) + (Ka + Kb) * N + 2 * M * N), 2.0 * M * (Ka + Kb) * N, "hbm"
@@ -223,6 +226,7 @@ OP_KERNEL = {
     "dh3d_flex_conv_pm": ("flexconv_ca_kernel",),
     "dh3d_flex_conv_pm_packed": ("flexconv_ca_kernel",),
     "dh3d_linear_join_packed": ("gemm_join16_kernel",),
+    "dh3d_linear_chain_packed": ("gemm_chain16_kernel",),
     "dh3d_se_pool_excite": ("se_pool_excite_kernel",),
 }
 

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "dh3d_linear_rowdot_packed": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_float, _c_int, _p, _c_int,
                                             _c_int, _c_int, _p]),
     "dh3d_rowdot": (_c_int, [_p, _c_int, _p, _c_float, _c_int, _p, _c_int, _c_int, _p]),
+    "dh3d_linear_chain_packed": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int,
+                                          _c_int, _c_int, _p]),
     "dh3d_linear_join_packed": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _p, _p, _p, _c_int, _p, _c_int,
                                          _p, _c_int, _c_float, _c_int, _c_int, _c_int, _c_int, _p]),
     "dh3d_se_excite": (_c_int, [_p, _p, _p, _c_size_t, _p]),

@@ -229,7 +229,17 @@ class AttentionHead(FoldedModule):
             fc = self.detec_conv_fc
             self._folded = (fc.W.reshape(-1).contiguous(), float(fc.b.reshape(-1)[0].item()))
         w2, b2 = self._folded
-        for i in range(self.n - 1):
+        i0 = 0
+        if self.n == 3 and USE_FUSED_BLOCKS:
+            # detection_block's 128 -> 128 -> 256 layers in one launch (dh3d_linear_chain_packed): the hidden
+            # [B*N,128] activation stays on the SM
+            c0, c1 = self.detec_conv0, self.detec_conv1
+            (_, s0, b0, p0), (_, s1, b1, p1) = c0.folded(), c1.folded()
+            if (p0 is not None and p1 is not None and
+                    ops.linear_chain_supported(c0.W.shape[2], c0.W.shape[3], c1.W.shape[3])):
+                x = ops.linear_chain(x, p0, s0, b0, c0.act, p1, s1, b1, c1.act)
+                i0 = 2
+        for i in range(i0, self.n - 1):
             x = getattr(self, "detec_conv%d" % i)(x)
         last = getattr(self, "detec_conv%d" % (self.n - 1))
         w, scale, shift, packed = last.folded()

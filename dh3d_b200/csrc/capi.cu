@@ -63,6 +63,9 @@ int linear_tc16_launch(const float* x, int ldx, const void* packed, const float*
 int linear_rowdot_tc16_launch(const float* x, int ldx, const void* packed, const float* scale,
                               const float* shift, int act, const float* w2, float b2, int act2, float* y2,
                               int M, int K, int N, cudaStream_t st);
+int linear_chain_tc16_launch(const float* x, int ldx, const void* packed1, const float* scale1, const float* shift1,
+                             int act1, const void* packed2, const float* scale2, const float* shift2, int act2,
+                             float* y, int ldy, int M, int K1, int N1, int N2, cudaStream_t st);
 int linear_join_tc16_launch(const float* xa, int ldxa, const void* packed_a, const float* scale_a,
                             const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_b,
                             const float* scale_b, const float* shift_b, int act_b, float* y, int ldy, float* yn,
@@ -298,6 +301,13 @@ int dh3d_linear_rowdot_packed(const float* x, int ldx, const void* packed_w, con
                               float* y, int M, int K, int N, void* stream) {
   return linear_rowdot_tc16_launch(x, ldx, packed_w, scale, shift, act, w2, b2, act2, y, M, K, N, S(stream));
 }
+int dh3d_linear_chain_packed(const float* x, int ldx, const void* packed_w1, const float* scale1, const float* shift1,
+                             int act1, const void* packed_w2, const float* scale2, const float* shift2, int act2,
+                             float* y, int ldy, int M, int K1, int N1, int N2, void* stream) {
+  return linear_chain_tc16_launch(x, ldx, packed_w1, scale1, shift1, act1, packed_w2, scale2, shift2, act2, y, ldy, M,
+                                  K1, N1, N2, S(stream));
+}
+
 int dh3d_linear_join_packed(const float* xa, int ldxa, const void* packed_wa, const float* scale_a,
                             const float* shift_a, int act_a, const float* xb, int ldxb, const void* packed_wb,
                             const float* scale_b, const float* shift_b, int act_b, float* y, int ldy,

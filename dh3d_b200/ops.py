@@ -278,6 +278,28 @@ def linear_join(xa, packed_a, scale_a, shift_a, act_a, xb, packed_b, scale_b, sh
     return (y, yn) if eps is not None else y
 
 
+def linear_chain_supported(K1, N1, N2):
+    """Shapes ``linear_chain`` is built for (dh3d_linear_chain_packed): K1 <= 128, N1 == 128, N2 <= 256."""
+    return 0 < K1 <= 128 and K1 % 4 == 0 and N1 == 128 and 0 < N2 <= 256 and N2 % 4 == 0
+
+
+def linear_chain(x, packed1, scale1, shift1, act1, packed2, scale2, shift2, act2):
+    """act2((act1((x @ W1)*scale1 + shift1) @ W2)*scale2 + shift2) in one launch; the hidden activation never
+    reaches HBM.  Weights as linear_prepack buffers of W1 [K1,128], W2 [128,N2]."""
+    M, K1 = _rows(x)
+    (Kp1, N1), (Kp2, N2) = packed1._dh3d_kn, packed2._dh3d_kn
+    if Kp1 != K1 or Kp2 != N1 or not linear_chain_supported(K1, N1, N2):
+        raise _lib.Dh3dError("linear_chain: unsupported shapes K1=%d N1=%d (W2 rows %d) N2=%d" % (K1, N1, Kp2, N2))
+    y = torch.empty(x.shape[:-1] + (N2,), dtype=f32, device=x.device)
+    _lib.stats.tag = "M%d_K%d_H%d_N%d" % (M, K1, N1, N2)
+    call("dh3d_linear_chain_packed", check(x, f32, "x"), K1, ctypes.c_void_p(packed1.data_ptr()),
+         opt(scale1, f32, "scale1"), opt(shift1, f32, "shift1"), int(act1), ctypes.c_void_p(packed2.data_ptr()),
+         opt(scale2, f32, "scale2"), opt(shift2, f32, "shift2"), int(act2), check(y, f32, "y"), N2, M, K1, N1, N2,
+         stream_ptr(x.device))
+    _lib.stats.tag = None
+    return y
+
+
 def _rows(x):
     """[..., C] contiguous tensor -> (M, C) row view parameters."""
     C = x.shape[-1]

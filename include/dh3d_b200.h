@@ -213,6 +213,17 @@ DH3D_API int dh3d_linear_join_packed(const float* xa, int ldxa, const void* pack
                             const void* packed_wb, const float* scale_b, const float* shift_b, int act_b,
                             float* y, int ldy, float* y_normalized, int ldn, float eps, int M, int Ka,
                             int Kb, int N, void* stream);
+/* Two chained 1x1 layers in one launch (detection_block's 128 -> 128 -> 256 stack, core/backbones.py:132-147):
+ *     y = act2( (act1((x @ W1)*scale1 + shift1) @ W2)*scale2 + shift2 )        x [M,K1] -> y [M,N2]
+ * the hidden [M,N1] activation stays on the SM.  packed_w1 / packed_w2 = dh3d_linear_prepack of W1 [K1,N1] /
+ * W2 [N1,N2].  Built for K1 <= 128, N1 == 128, N2 <= 256 (multiples of 4); other shapes return
+ * DH3D_ERR_UNSUPPORTED and the caller composes dh3d_linear_packed x2.  Same accuracy and out-of-window-row
+ * guarantee as dh3d_linear_packed (rows whose input OR hidden activations leave the fp16-pair window are
+ * recomputed through both layers in fp32). */
+DH3D_API int dh3d_linear_chain_packed(const float* x, int ldx, const void* packed_w1, const float* scale1,
+                             const float* shift1, int act1, const void* packed_w2, const float* scale2,
+                             const float* shift2, int act2, float* y, int ldy, int M, int K1, int N1, int N2,
+                             void* stream);
 DH3D_API int dh3d_rowdot(const float* x, int ldx, const float* w, float bias, int act, float* y, int M,
                 int K, void* stream);
 DH3D_API int dh3d_se_excite(const float* x, const float* gate, float* y, size_t count, void* stream);

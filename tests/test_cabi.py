@@ -82,6 +82,19 @@ def test_argument_validation_happens_before_any_cuda_call():
                                        128, f(1e-8), 8, 192, 64, 128, null) == -1
     assert lib.dh3d_linear_join_packed(one, 190, one, null, null, 1, one, 64, one, null, null, 1, one, 128, null,
                                        128, f(1e-8), 8, 190, 64, 128, null) == -2                       # K % 4
+    # chained two-layer entry: x, ldx, packed1, scale1, shift1, act1, packed2, scale2, shift2, act2, y, ldy, M, K1, N1, N2
+    assert lib.dh3d_linear_chain_packed(one, 128, one, null, null, 1, one, null, null, 1, one, 256, 8, 128, 64, 256,
+                                        null) == -3                                                     # N1 != 128
+    assert lib.dh3d_linear_chain_packed(one, 256, one, null, null, 1, one, null, null, 1, one, 256, 8, 256, 128, 256,
+                                        null) == -3                                                     # K1 > 128
+    assert lib.dh3d_linear_chain_packed(one, 128, one, null, null, 1, one, null, null, 1, one, 512, 8, 128, 128, 512,
+                                        null) == -3                                                     # N2 > 256
+    assert lib.dh3d_linear_chain_packed(null, 128, one, null, null, 1, one, null, null, 1, one, 256, 8, 128, 128, 256,
+                                        null) == -1
+    assert lib.dh3d_linear_chain_packed(one, 128, one, null, null, 1, null, null, null, 1, one, 256, 8, 128, 128, 256,
+                                        null) == -1
+    assert lib.dh3d_linear_chain_packed(one, 128, one, null, null, 1, one, null, null, 1, one, 200, 8, 128, 128, 256,
+                                        null) == -2                                                     # ldy < N2
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 128, 64, 256) == 0                      # unsupported dims
     assert lib.dh3d_netvlad_workspace_bytes(2, 100, 256, 64, 256) > 0
 

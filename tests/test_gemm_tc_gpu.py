@@ -229,3 +229,64 @@ def test_linear_join_vs_fp64_and_unfused(M, Ka, Kb):
     assert (yn - ops.l2_normalize_rows(y, 1e-8)).abs().max().item() <= 1e-6
     only = ops.linear_join(t(xa), pa, t(sa), t(ba), 1, t(xb), pb, t(sb), t(bb), 1)
     assert torch.equal(only, y)
+
+
+@pytest.mark.parametrize("M,K1,N2", [(1000, 128, 256), (128 * 149 + 5, 128, 256), (300, 64, 128), (4096, 36, 200),
+                                     (128 * 300, 128, 256)])
+def test_linear_chain_vs_fp64_and_unfused(M, K1, N2):
+    """dh3d_linear_chain_packed: relu(BN(relu(BN(x@W1))@W2)) in one launch (detection_block's 128 -> 128 -> 256 layers,
+    core/backbones.py:132-147) against fp64 and against the two separate launches."""
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(M + K1 + N2)
+    N1 = 128
+    x = rng.randn(M, K1).astype(np.float32)
+    w1, w2 = (rng.randn(K1, N1) / np.sqrt(K1)).astype(np.float32), (rng.randn(N1, N2) / np.sqrt(N1)).astype(np.float32)
+    s1, s2 = (rng.rand(N1) + 0.5).astype(np.float32), (rng.rand(N2) + 0.5).astype(np.float32)
+    b1, b2 = (rng.randn(N1) * 0.3).astype(np.float32), (rng.randn(N2) * 0.3).astype(np.float32)
+    t = lambda a: torch.from_numpy(a).cuda()
+    p1, p2 = ops.linear_prepack(t(w1)), ops.linear_prepack(t(w2))
+    y = ops.linear_chain(t(x), p1, t(s1), t(b1), 1, p2, t(s2), t(b2), 1)
+    h = np.maximum(x.astype(np.float64) @ w1 * s1 + b1, 0)
+    want = np.maximum(h @ w2 * s2 + b2, 0)
+    scale = np.sqrt(np.mean(want ** 2))
+    assert y.shape == (M, N2)
+    assert np.abs(y.cpu().numpy() - want).max() <= 1e-4 * scale + 1e-4 * np.abs(want).max()
+    u = ops.linear(ops.linear(t(x), t(w1), scale=t(s1), shift=t(b1), act=1, packed=p1), t(w2), scale=t(s2), shift=t(b2),
+                   act=1, packed=p2)
+    assert (y - u).abs().max().item() <= 2e-5 * scale
+    # no activation / no affine on either layer
+    y0 = ops.linear_chain(t(x), p1, None, None, 0, p2, None, None, 0).cpu().numpy()
+    want0 = (x.astype(np.float64) @ w1) @ w2
+    assert np.abs(y0 - want0).max() <= 1e-4 * np.sqrt(np.mean(want0 ** 2)) + 1e-4 * np.abs(want0).max()
+
+
+def test_linear_chain_out_of_window_rows_both_layers():
+    """Rows whose INPUT leaves the fp16-pair window, and rows whose HIDDEN activation does (a large first-layer scale on
+    in-window inputs), are recomputed through both layers in fp32: every row within 1e-4 of fp64 relative to its own
+    scale; inf / NaN stay in their row."""
+    from dh3d_b200 import ops
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x = _range_case(31, 128 * 37 + 3, 128)
+    M = x.shape[0]
+    rng = np.random.RandomState(5)
+    w1, w2 = (rng.randn(128, 128) / np.sqrt(128)).astype(np.float32), (rng.randn(128, 256) / np.sqrt(128)).astype(np.float32)
+    p1, p2 = ops.linear_prepack(t(w1)), ops.linear_prepack(t(w2))
+    y = ops.linear_chain(t(x), p1, None, None, 1, p2, None, None, 0).cpu().numpy()
+    want = np.maximum(x.astype(np.float64) @ w1, 0) @ w2
+    assert np.isfinite(y).all()
+    assert _rowwise_rel_err(y, want) < 1e-4, _rowwise_rel_err(y, want)
+    # hidden rows out of the window: ordinary inputs, first-layer scale 1e5 on a third of the rows' worth of columns
+    xs = rng.randn(5000, 128).astype(np.float32)
+    s1 = np.ones(128, np.float32)
+    s1[::3] = 1e5
+    y = ops.linear_chain(t(xs), p1, t(s1), None, 1, p2, None, None, 0).cpu().numpy()
+    want = np.maximum(xs.astype(np.float64) @ w1 * s1, 0) @ w2
+    assert np.isfinite(y).all()
+    assert _rowwise_rel_err(y, want) < 1e-4, _rowwise_rel_err(y, want)
+    # non-finite input row: that row only
+    xs[77, 5] = np.inf
+    y = ops.linear_chain(t(xs), p1, None, None, 1, p2, None, None, 0).cpu().numpy()
+    assert not np.isfinite(y[77]).all()
+    ok = np.delete(np.arange(5000), 77)
+    want = np.maximum(np.delete(xs, 77, 0).astype(np.float64) @ w1, 0) @ w2
+    assert np.isfinite(y[ok]).all() and _rowwise_rel_err(y[ok], want) < 1e-4

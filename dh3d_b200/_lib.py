@@ -43,6 +43,7 @@ _SIGNATURES = {
     "dh3d_three_nn": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p]),
     "dh3d_three_nn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "dh3d_three_nn_ws": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _c_size_t, _p]),
+    "dh3d_three_nn_ws_presorted": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _c_size_t, _p]),
     "dh3d_three_interpolate": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_three_interpolate_from_dist": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_linear": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p]),
@@ -97,7 +98,7 @@ _KERNELS_PER_CALL = {
     "dh3d_flex_conv": 8,                                             # 4 transposes + 2 theta_ext + fold_bias + fused kernel
     "dh3d_flex_conv_pm": 4,                                          # 2 theta_ext forms + fold_bias + the fused kernel
     "dh3d_flex_conv_prepack": 3, "dh3d_flex_conv_pm_packed": 1,      # weights once; then the fused kernel only
-    "dh3d_query_ball_point": 2, "dh3d_netvlad": 3, "dh3d_three_nn_ws": 3,   # netvlad: cluster-weight prepack + aggregate + tail
+    "dh3d_query_ball_point": 2, "dh3d_netvlad": 3, "dh3d_three_nn_ws": 3, "dh3d_three_nn_ws_presorted": 2,   # netvlad: cluster-weight prepack + aggregate + tail
     "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
     "dh3d_keypoint_nms": 5,
 }

@@ -674,29 +674,46 @@ size_t three_nn_workspace_bytes(int b, int n, int m) {
   return (size_t)b * (np2 + knn_box_f4(np2) + np1 + knn_box_f4(np1)) * sizeof(float4);
 }
 
-int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
-                           int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (!xyz1 || !xyz2 || !dist || !idx) return DH3D_ERR_NULL;
+// sorted1: optional -- the query cloud as the k-NN of the same points left it at the start of its workspace (float4
+// (x,y,z,index) [b][knn_padded(n)], any cell order): the query sort is then skipped (DH3D runs the k-NN of the dense
+// cloud anyway; its sort is 30 us of the side stream's chain)
+static int three_nn_pruned_impl(int b, int n, int m, const float* xyz1, const float4* sorted1, const float* xyz2,
+                                float* dist, int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if ((!xyz1 && !sorted1) || !xyz2 || !dist || !idx) return DH3D_ERR_NULL;
   if (b <= 0 || n <= 0 || m <= 0) return DH3D_ERR_DIM;
   if (b > 65535) return DH3D_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < three_nn_workspace_bytes(b, n, m)) return DH3D_ERR_WORKSPACE;
-  if (((uintptr_t)workspace & 127) != 0) return DH3D_ERR_ALIGN;
+  if ((((uintptr_t)workspace | (uintptr_t)sorted1) & 127) != 0) return DH3D_ERR_ALIGN;
   const int np1 = knn_padded(n), np2 = knn_padded(m);
   float4* cands = reinterpret_cast<float4*>(workspace);
   float4* boxes = cands + (size_t)b * np2;
   float4* queries = boxes + (size_t)b * knn_box_f4(np2);
   float4* qboxes = queries + (size_t)b * np1;
+  int rc;
   // tie rank of the 3-NN metric = the index itself (T = 2^30, V = 1)
-  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, 1 << 30, 30, 0, queries, qboxes);
-  int rc = launch_status();
-  if (rc != DH3D_OK) return rc;
+  if (!sorted1) {
+    knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, 1 << 30, 30, 0, queries, qboxes);
+    if ((rc = launch_status()) != DH3D_OK) return rc;
+  }
   knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, 1 << 30, 30, 0, cands, boxes);
   rc = launch_status();
   if (rc != DH3D_OK) return rc;
   dim3 grid(ceil_div(np1, kKnnThreads), b);
   knn_query_kernel<4, false, false, ThreeNnMetric><<<grid, kKnnThreads, 0, st>>>(
-      queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, idx, dist);
+      sorted1 ? sorted1 : queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, idx, dist);
   return launch_status();
+}
+
+int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
+                           int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  return three_nn_pruned_impl(b, n, m, xyz1, nullptr, xyz2, dist, idx, workspace, workspace_bytes, st);
+}
+
+int three_nn_presorted_launch(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2, float* dist,
+                              int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!knn_workspace_of_xyz1) return DH3D_ERR_NULL;
+  return three_nn_pruned_impl(b, n, m, nullptr, reinterpret_cast<const float4*>(knn_workspace_of_xyz1), xyz2, dist, idx,
+                              workspace, workspace_bytes, st);
 }
 
 }  // namespace dh3d

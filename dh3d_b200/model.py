@@ -68,27 +68,33 @@ class DH3D(nn.Module):
         same_geometry = c.extract_global and c.gl_dilate == c.dilate
         cur = torch.cuda.current_stream(points.device)
 
-        # xyz-only geometry (FPS chain is latency-bound and independent of stage 1): side stream
-        geometry = None
+        # xyz-only geometry (FPS chain is latency-bound and independent of stage 1): side stream.  The side stream's
+        # 3-NN walks the cell-sorted copy of the cloud that the main stream's k-NN leaves in its workspace.
+        geometry, sorted_xyz, sorted_ready = None, None, None
         if overlap:
             if self._side is None or self._side.device != points.device:
                 self._side = torch.cuda.Stream(device=points.device)
-            self._side.wait_stream(cur)
+            self._side.wait_stream(cur)     # (before the k-NN is enqueued: the side stream starts next to it)
+        if knn_inds is None:
+            knn_inds, _, sorted_xyz = ops.knn_points(points, c.knn_num, keep_workspace=True)
+            if overlap:
+                sorted_ready = torch.cuda.Event()
+                sorted_ready.record(cur)
+        if overlap:
             with torch.cuda.stream(self._side):
-                geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
+                geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num, sorted_xyz, sorted_ready)
                 # the main stream joins where the geometry is first consumed (stage 2's group_point), so the
                 # k-NN of the sampled points and the 3-NN run next to stage 1 instead of in front of it
                 geometry.ready = torch.cuda.Event()
                 geometry.ready.record(self._side)
-        if knn_inds is None:
-            knn_inds, _ = ops.knn_points(points, c.knn_num)
-        if overlap:
             if not torch.cuda.is_current_stream_capturing():
                 for t in (geometry.kp_indices, geometry.points_sampled, geometry.knn_indices,
                           geometry.nn_dist, geometry.nn_idx):
                     t.record_stream(cur)
+                if sorted_xyz is not None:
+                    sorted_xyz.record_stream(self._side)
         else:
-            geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num)
+            geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num, sorted_xyz)
 
         want = set(outputs)
         given = out or {}

@@ -16,8 +16,10 @@ f32, i32 = torch.float32, torch.int32
 _ci, _cf, _cs = ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
 
-def knn_points(xyz, k):
-    """xyz [B,N,3] -> (ids [B,N,K] i32, dists [B,N,K] f32).  Reference order and ties, see knn.cu."""
+def knn_points(xyz, k, keep_workspace=False):
+    """xyz [B,N,3] -> (ids [B,N,K] i32, dists [B,N,K] f32).  Reference order and ties, see knn.cu.
+    keep_workspace=True also returns the call's workspace tensor: it starts with the cell-sorted copy of the cloud,
+    which ``three_nn(..., sorted1=...)`` can walk instead of sorting the same points again."""
     px = check(xyz, f32, "xyz", 3)
     B, N, D = xyz.shape
     if D != 3:
@@ -29,6 +31,9 @@ def knn_points(xyz, k):
     call("dh3d_knn_bruteforce_pm", px, B, N, int(k), check(ids, i32, "ids"), check(dists, f32, "dists"),
          wp, wn, stream_ptr(xyz.device))
     _lib.stats.tag = None
+    if keep_workspace:
+        ws._dh3d_sorted_of = (B, N)
+        return ids, dists, ws
     return ids, dists
 
 
@@ -192,9 +197,10 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
-def three_nn(xyz1, xyz2, exhaustive=False):
+def three_nn(xyz1, xyz2, exhaustive=False, sorted1=None):
     """3 nearest xyz2 points of every xyz1 point (squared distances, reference arithmetic and ties).
-    Default: Morton-sorted box-pruned scan (same results); exhaustive=True: the plain tiled scan."""
+    Default: Morton-sorted box-pruned scan (same results); exhaustive=True: the plain tiled scan.
+    sorted1: the workspace ``knn_points(xyz1, k, keep_workspace=True)`` returned (skips the sort of xyz1)."""
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     dist = torch.empty((B, n, 3), dtype=f32, device=xyz1.device)
@@ -205,6 +211,13 @@ def three_nn(xyz1, xyz2, exhaustive=False):
         return dist, idx
     ws, wp, wn = workspace(query("dh3d_three_nn_workspace_bytes", B, n, m), xyz1.device)
     _lib.stats.tag = "B%d_n%d_m%d" % (B, n, m)
+    if sorted1 is not None:
+        if getattr(sorted1, "_dh3d_sorted_of", None) != (B, n):
+            raise _lib.Dh3dError("three_nn: sorted1 is not the k-NN workspace of a [%d,%d,3] cloud" % (B, n))
+        call("dh3d_three_nn_ws_presorted", B, n, m, ctypes.c_void_p(sorted1.data_ptr()), check(xyz2, f32, "xyz2", 3),
+             check(dist, f32, "dist"), check(idx, i32, "idx"), wp, wn, stream_ptr(xyz1.device))
+        _lib.stats.tag = None
+        return dist, idx
     call("dh3d_three_nn_ws", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
          check(dist, f32, "dist"), check(idx, i32, "idx"), wp, wn, stream_ptr(xyz1.device))
     _lib.stats.tag = None

@@ -164,6 +164,12 @@ DH3D_API int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* 
 DH3D_API size_t dh3d_three_nn_workspace_bytes(int b, int n, int m);
 DH3D_API int dh3d_three_nn_ws(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
                      int32_t* idx, void* workspace, size_t workspace_bytes, void* stream);
+/* dh3d_three_nn_ws with the QUERY cloud already sorted: knn_workspace_of_xyz1 = the workspace a dh3d_knn_bruteforce_pm
+ * call on the same xyz1 [b,n,3] left behind (it starts with the cell-sorted (x,y,z,index) array this scan walks), so
+ * the query sort is skipped -- DH3D's forward runs the k-NN of the dense cloud anyway (core/model.py:157).  Same
+ * results as dh3d_three_nn / dh3d_three_nn_ws; the workspace of THIS call as for dh3d_three_nn_ws. */
+DH3D_API int dh3d_three_nn_ws_presorted(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2,
+                               float* dist, int32_t* idx, void* workspace, size_t workspace_bytes, void* stream);
 DH3D_API int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
                            const float* weight, float* out, void* stream);
 /* fused caller-side step of core/backbones.py:91-96: weight = (1/max(d,1e-10))/sum(...) computed

@@ -442,3 +442,23 @@ def test_strided_group_interp_and_add_l2norm_are_bit_identical_to_the_unfused_op
     s, nrm = ops.add_l2_normalize_rows(x, y, 1e-8)
     assert torch.equal(s, ops.add(x, y))
     assert torch.equal(nrm, ops.l2_normalize_rows(ops.add(x, y), 1e-8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,n,m", [(2, 8192, 1024), (3, 1000, 77), (1, 4097, 512)])
+def test_three_nn_presorted_queries_bit_exact(B, n, m):
+    """dh3d_three_nn_ws_presorted: the query cloud's sort is taken from the workspace a k-NN call on the same points left
+    behind (what DH3D.forward does); distances and indices identical to the exhaustive scan and to the self-sorting form."""
+    from dh3d_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + n)
+    xyz1 = (torch.rand((B, n, 3), device="cuda", generator=g) * 40 - 20).contiguous()
+    xyz1[0, : n // 8] = xyz1[0, n // 8: 2 * (n // 8)]          # duplicated points (distance ties)
+    xyz2 = xyz1[:, torch.randperm(n, device="cuda", generator=g)[:m]].contiguous()
+    _, _, ws = ops.knn_points(xyz1, 8, keep_workspace=True)
+    d0, i0 = ops.three_nn(xyz1, xyz2, exhaustive=True)
+    d1, i1 = ops.three_nn(xyz1, xyz2)
+    d2, i2 = ops.three_nn(xyz1, xyz2, sorted1=ws)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)
+    assert torch.equal(i0, i2) and torch.equal(d0, d2)
+    with pytest.raises(Exception):
+        ops.three_nn(xyz1[:, :-1].contiguous(), xyz2, sorted1=ws)      # workspace of another shape

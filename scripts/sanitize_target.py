@@ -37,6 +37,8 @@ if want("three_nn"):
     kp = ops.farthest_point_sample(256, pts)
     m = ops.gather_point(pts, kp)
     d, i = ops.three_nn(pts, m)
+    _, _, ws = ops.knn_points(pts, 8, keep_workspace=True)
+    ops.three_nn(pts, m, sorted1=ws)                    # query sort taken from the k-NN workspace
     ops.three_interpolate(rnd(2, 256, 128), i, d, weight_is_dist2=True)
     print("three_nn ok")
 if want("flexconv"):
@@ -68,6 +70,14 @@ if want("gemm"):
     xa[5] *= 1e5
     ops.linear_join(xa, ops.linear_prepack(rnd(192, 128) / 14), None, None, 1, xb, ops.linear_prepack(rnd(64, 128) / 8),
                     None, None, 1, eps=1e-8)
+    xc = rnd(4200, 128)
+    xc[9] *= 1e6          # out-of-window input row; column scale 1e5 below pushes hidden rows out of the window too
+    sc = torch.ones(128, device="cuda")
+    sc[::5] = 1e5
+    ops.linear_chain(xc, ops.linear_prepack(rnd(128, 128) / 11), None, None, 1, ops.linear_prepack(rnd(128, 256) / 11),
+                     None, None, 1)
+    ops.linear_chain(xc[:700].contiguous(), ops.linear_prepack(rnd(128, 128) / 11), sc, None, 1,
+                     ops.linear_prepack(rnd(128, 256) / 11), None, None, 0)
     ops.linear(rnd(1000, 64), rnd(64, 16) / 8)     # FFMA kernel
     print("gemm ok")
 if want("netvlad"):

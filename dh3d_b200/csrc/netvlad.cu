@@ -140,7 +140,7 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
 // Three phases of one persistent kernel (was three launches: 17 + 31 + 33 us for 32 clouds, each mostly launch ramp and
 // load latency), separated by grid barriers on a counter in the workspace (every CTA is resident: grid <= SM count,
 // one 256-thread CTA each).  Data written in one phase is read in the next with plain (coherent) loads.
-constexpr int kVQ = 16;
+constexpr int kVQ = 8;     // clusters per phase-A work item: B * 8 items = one per CTA at B = 32
 
 __device__ __forceinline__ void nv_grid_barrier(unsigned int* ctr, unsigned int target) {
   __syncthreads();
@@ -148,14 +148,15 @@ __device__ __forceinline__ void nv_grid_barrier(unsigned int* ctr, unsigned int 
     __threadfence();
     atomicAdd(ctr, 1u);
     unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    do {   // relaxed polls (an acquire load costs a cache invalidation per poll), one fence once the count is in
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     } while (v < target);
+    __threadfence();
   }
   __syncthreads();
 }
 
-// phase A, work item (b, q): clusters 16q .. 16q+15 of cloud b; thread = feature d.  Combines the slabs, subtracts
+// phase A, work item (b, q): clusters 8q .. 8q+7 of cloud b; thread = feature d.  Combines the slabs, subtracts
 // S*W2, intra-normalises each cluster column (over the 256 features, inside the CTA) and writes the feature-major
 // flattening ([d*64 + k], backbones.py:258-260).  The global l2 norm of the flattened vector only needs the 64
 // column norms: they go to coln[b][k] and the scalar is applied after the (linear) projection, in phase C.

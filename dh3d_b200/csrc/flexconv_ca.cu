@@ -42,15 +42,19 @@ constexpr uint32_t kCAStageBytes = 128 * 128;   // 128 rows x 32 channels fp32
 // K8 = the K == 8 fast path (every FlexConv of DH3D): the neighbour loop is fully unrolled, so the ring slot, the
 // table slot and the operand stage of every item are compile-time constants and the issue cursor advances at one
 // static point per group (see the consumer branch).
-template <int BN, int NB>   // NB = K / 8 for the unrolled 8-slot schedule (K = 8, 16, 32), 0 = generic loop (any K)
+// NB = K / 8 for the unrolled 8-slot schedule (K = 8, 16, 32), 0 = generic loop (any K).
+// NF = output tiles fed from ONE set of moment slabs: for Dout = 2 * BN the gather used to run once per N tile; with
+// NF = 2 every A slab is multiplied against both Theta tiles (two accumulators live, all 512 TMEM columns with the
+// double buffering), so the neighbour rows are gathered once.
+template <int BN, int NB, int NF = 1>
 struct CACfg {
   static constexpr bool K8 = NB > 0;
   static constexpr int kStages = 2;                           // UMMA A-operand stages (moment slabs, hi + lo)
   // Theta tiles have their OWN ring, decoupled from the A stages: with the tiles inside the A stages (r1) the TMA of
   // slab i + 2 could only be issued once the MMAs of slab i had completed, so every slab paid an L2 round trip
-  static constexpr int kBStages = K8 ? (BN <= 64 ? 4 : 2) : 2;
+  static constexpr int kBStages = NF > 1 ? 3 : (K8 ? (BN <= 64 ? 4 : 2) : 2);
   // gather stages (16 KB each): ring depth 6 / 3 / 2 measured within 10 % of each other (profiles/flexconv_*_r2s.txt)
-  static constexpr int kGStages = K8 ? 4 : (BN <= 64 ? 5 : 3);
+  static constexpr int kGStages = NF > 1 ? 2 : (K8 ? 4 : (BN <= 64 ? 5 : 3));
   static constexpr int kOutRows = K8 ? 16 : 32;  // rows per epilogue TMA store (smem budget)
   static constexpr uint32_t kOutBytes = 4 * kOutRows * 32 * 4;
   static constexpr uint32_t kBBytes = BN * kTcBK * 4;
@@ -58,21 +62,23 @@ struct CACfg {
   static constexpr uint32_t kBStageBytes = 2 * kBBytes;
   static constexpr uint32_t kDeltaBytes = 128 * kCAKB * 16;   // float4 per (row, slot)
   static constexpr uint32_t kIdxBytes = 128 * kCAKB * 4;      // global feature row per (row, slot)
-  static constexpr uint32_t kParamBytes = 2 * 2 * BN * 4;     // double-buffered scale/shift slices
+  static constexpr uint32_t kParamBytes = 2 * 2 * NF * BN * 4;   // double-buffered scale/shift slices
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBStages * kBStageBytes + kGStages * kCAStageBytes +
                                          kDeltaBytes + kIdxBytes + kOutBytes + kParamBytes + 256 /*barriers*/ +
                                          1024 /*align*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget (227 KB)");
-  static constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t kTmemCols = 2 * NF * BN < 32 ? 32 : 2 * NF * BN;
+  static_assert(kTmemCols <= 512 && (NF == 1 || NB > 0), "NF > 1: unrolled schedule only, 512 TMEM columns");
 };
 
-template <int BN, int NB>
+template <int BN, int NB, int NF = 1>
 __global__ void __launch_bounds__(kCAThreads, 1)
 flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY,
                    const CAArgs a) {
-  using Cfg = CACfg<BN, NB>;
+  using Cfg = CACfg<BN, NB, NF>;
   constexpr bool K8 = NB > 0;
+  constexpr int W = NF * BN;          // output columns per accumulator set
   constexpr int S = Cfg::kStages;
   constexpr int SB = Cfg::kBStages;
   constexpr int G = Cfg::kGStages;
@@ -95,7 +101,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_mt = (a.rows + kTcBM - 1) / kTcBM;
-  const int num_nt = (a.Dout + BN - 1) / BN;
+  const int num_nt = (a.Dout + W - 1) / W;   // accumulator sets (NF tiles of BN columns each) per row tile
   const int num_cg = a.Din / kTcBK;     // 32-channel groups; 4 K-slabs each
   const int num_kb = 4 * num_cg;
   const int num_batches = (a.K + kCAKB - 1) / kCAKB;
@@ -139,46 +145,51 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
       for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
         for (int nt = 0; nt < num_nt; ++nt)
           for (int cg = 0; cg < num_cg; ++cg)
-            for (int p = 0; p < 4; ++p, ++it) {
-              const int s = it % SB;
-              const uint32_t ph = (it / SB) & 1;
-              mbar_wait(&bempty[s], ph ^ 1);
-              mbar_arrive_expect_tx(&bfull[s], 2 * Cfg::kBBytes);
-              const int k0 = p * a.Din + cg * kTcBK;  // row block of Theta_ext == column block of Theta_ext^T
-              tma_load_2d(stage_bhi(s), &tmBhi, k0, nt * BN, &bfull[s]);
-              tma_load_2d(stage_blo(s), &tmBlo, k0, nt * BN, &bfull[s]);
-            }
+            for (int p = 0; p < 4; ++p)
+              for (int f = 0; f < NF; ++f, ++it) {
+                const int s = it % SB;
+                const uint32_t ph = (it / SB) & 1;
+                mbar_wait(&bempty[s], ph ^ 1);
+                mbar_arrive_expect_tx(&bfull[s], 2 * Cfg::kBBytes);
+                const int k0 = p * a.Din + cg * kTcBK;  // row block of Theta_ext == column block of Theta_ext^T
+                tma_load_2d(stage_bhi(s), &tmBhi, k0, nt * W + f * BN, &bfull[s]);
+                tma_load_2d(stage_blo(s), &tmBlo, k0, nt * W + f * BN, &bfull[s]);
+              }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(kTcBM >> 4) << 24);
-      uint32_t it = 0, tile = 0;
+      uint32_t it = 0, itb = 0, tile = 0;
       for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
         for (int nt = 0; nt < num_nt; ++nt, ++tile) {
           const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
           mbar_wait(&tmem_empty[acc], aph ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmem_d = tmem_base + acc * BN;
+          const uint32_t tmem_d = tmem_base + acc * W;
           for (int kb = 0; kb < num_kb; ++kb, ++it) {
-            const int s = it % S, sb = it % SB;
-            mbar_wait(&bfull[sb], (it / SB) & 1);
+            const int s = it % S;
             mbar_wait(&afull[s], (it / S) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_hi = umma_desc_sw128(smem_u32(stage_a(s)));
             const uint64_t a_lo = umma_desc_sw128(smem_u32(stage_alo(s)));
-            const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_bhi(sb)));
-            const uint64_t b_lo = umma_desc_sw128(smem_u32(stage_blo(sb)));
 #pragma unroll
-            for (int k = 0; k < kTcBK / 8; ++k) {
-              const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;
-              umma_tf32(tmem_d, a_lo + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_tf32(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
-              umma_tf32(tmem_d, a_hi + off, b_hi + off, idesc, 1u);
+            for (int f = 0; f < NF; ++f, ++itb) {
+              const int sb = itb % SB;
+              mbar_wait(&bfull[sb], (itb / SB) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint64_t b_hi = umma_desc_sw128(smem_u32(stage_bhi(sb)));
+              const uint64_t b_lo = umma_desc_sw128(smem_u32(stage_blo(sb)));
+#pragma unroll
+              for (int k = 0; k < kTcBK / 8; ++k) {
+                const uint64_t off = (uint64_t)(k * 8 * 4) >> 4;
+                umma_tf32(tmem_d + f * BN, a_lo + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_tf32(tmem_d + f * BN, a_hi + off, b_lo + off, idesc, 1u);
+                umma_tf32(tmem_d + f * BN, a_hi + off, b_hi + off, idesc, 1u);
+              }
+              umma_commit(&bempty[sb]);
             }
             umma_commit(&empty[s]);
-            umma_commit(&bempty[sb]);
           }
           umma_commit(&tmem_full[acc]);
         }
@@ -460,31 +471,31 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
     for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x)
       for (int nt = 0; nt < num_nt; ++nt, ++tile) {
         const uint32_t acc = tile & 1, aph = (tile >> 1) & 1;
-        float* prm = params + acc * 2 * BN;
-        for (int c = et; c < BN; c += 128) {
-          const int gc = nt * BN + c;
+        float* prm = params + acc * 2 * W;
+        for (int c = et; c < W; c += 128) {
+          const int gc = nt * W + c;
           const bool in = gc < a.Dout;
           prm[c] = (in && a.scale) ? __ldg(a.scale + gc) : 1.f;
-          prm[BN + c] = (in && a.shift) ? __ldg(a.shift + gc) : 0.f;
+          prm[W + c] = (in && a.shift) ? __ldg(a.shift + gc) : 0.f;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&tmem_full[acc], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0e = 0; c0e < BN; c0e += 32) {
+        for (int c0e = 0; c0e < W; c0e += 32) {
           uint32_t rg[32];
-          const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0e;
+          const uint32_t taddr = tmem_base + acc * W + ((uint32_t)(q * 32) << 16) + (uint32_t)c0e;
           DH3D_TMEM_LD_32X32(rg, taddr);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c0e + 32 >= BN) {
+          if (c0e + 32 >= W) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          if (nt * BN + c0e < a.Dout) {
+          if (nt * W + c0e < a.Dout) {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rg[j]), prm[c0e + j], prm[BN + c0e + j]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rg[j]), prm[c0e + j], prm[W + c0e + j]);
             tc_act32(v, a.act);
 #pragma unroll
             for (int pass = 0; pass < 32 / OR; ++pass) {
@@ -500,7 +511,7 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                tma_store_2d(&tmY, my_stage, nt * BN + c0e, mt * kTcBM + q * 32 + pass * OR);
+                tma_store_2d(&tmY, my_stage, nt * W + c0e, mt * kTcBM + q * 32 + pass * OR);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
               }
             }
@@ -520,16 +531,16 @@ flexconv_ca_kernel(const __grid_constant__ CUtensorMap tmBhi,
   }
 }
 
-template <int BN, int NB>
+template <int BN, int NB, int NF = 1>
 static int launch_ca(const CAArgs& a, const float* thi, const float* tlo, float* out, cudaStream_t st) {
-  using Cfg = CACfg<BN, NB>;
+  using Cfg = CACfg<BN, NB, NF>;
   CUtensorMap mh, ml, my;
   int rc;
   const int Kd = 4 * a.Din;
   if ((rc = make_map(&mh, thi, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
   if ((rc = make_map(&ml, tlo, a.Dout, Kd, Kd, BN)) != DH3D_OK) return rc;
   if ((rc = make_map(&my, out, a.rows, a.Dout, a.Dout, Cfg::kOutRows)) != DH3D_OK) return rc;
-  auto kern = flexconv_ca_kernel<BN, NB>;
+  auto kern = flexconv_ca_kernel<BN, NB, NF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::kSmemBytes);
   if (e != cudaSuccess) return (int)e;
@@ -549,6 +560,7 @@ int flexconv_ca_launch(const float* feat, const float* xyz, const int32_t* nbr, 
   const float* tlo = reinterpret_cast<const float*>(reinterpret_cast<const char*>(theta_packed) +
                                                     align_up((size_t)4 * Din * Dout * sizeof(float), 256));
   if (((uintptr_t)nbr & 7) == 0) {   // unrolled 8-slot schedule, K / 8 batches per group
+    if (K == 8 && Dout > 128 && Dout <= 256) return launch_ca<128, 1, 2>(a, thi, tlo, out, st);   // one gather, two N tiles
     if (K == 8) return Dout <= 64 ? launch_ca<64, 1>(a, thi, tlo, out, st) : launch_ca<128, 1>(a, thi, tlo, out, st);
     if (K == 16) return Dout <= 64 ? launch_ca<64, 2>(a, thi, tlo, out, st) : launch_ca<128, 2>(a, thi, tlo, out, st);
     if (K == 32) return Dout <= 64 ? launch_ca<64, 4>(a, thi, tlo, out, st) : launch_ca<128, 4>(a, thi, tlo, out, st);

@@ -35,6 +35,9 @@ _SIGNATURES = {
     "dh3d_conv_pointset": (_c_int, [_p] * 5 + [_c_int] * 5 + [_p]),
     "dh3d_conv_pointset_pm": (_c_int, [_p] * 5 + [_c_int] * 5 + [_p, _p, _c_int, _p]),
     "dh3d_farthest_point_sample": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p]),
+    "dh3d_farthest_point_sample_presorted": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p]),
+    "dh3d_knn_sort_pm": (_c_int, [_p, _c_int, _c_int, _p, _c_size_t, _p]),
+    "dh3d_knn_query_sorted": (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p, _p]),
     "dh3d_gather_point": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p]),
     "dh3d_group_point": (_c_int, [_c_int] * 5 + [_p, _p, _p, _p]),
     "dh3d_query_ball_point_workspace_bytes": (_c_size_t, [_c_int, _c_int]),

@@ -44,13 +44,14 @@ class DilateGeometry(object):
             self.ready = None
 
     def __init__(self, xyz, npoint, knn, sorted_xyz=None, sorted_ready=None):
-        """sorted_xyz: the workspace of the k-NN call on ``xyz`` (``ops.knn_points(..., keep_workspace=True)``), written
-        possibly on another stream; sorted_ready: the event after which it may be read there.  The 3-NN then skips its own sort."""
-        self.kp_indices = ops.farthest_point_sample(npoint, xyz)              # [B,M]
-        self.points_sampled = ops.gather_point(xyz, self.kp_indices)          # [B,M,3]
-        self.knn_indices, _ = ops.knn_points(self.points_sampled, knn)        # [B,M,K]
+        """sorted_xyz: the k-NN engine's cell-sorted copy of ``xyz`` (``ops.knn_sort`` / ``ops.knn_points(...,
+        keep_workspace=True)``): FPS then runs its box-pruned kernel on it and the 3-NN skips its own sort of the dense
+        cloud.  sorted_ready: the event after which that copy may be read, if it was written on another stream."""
         if sorted_ready is not None:
             torch.cuda.current_stream(xyz.device).wait_event(sorted_ready)
+        self.kp_indices = ops.farthest_point_sample(npoint, xyz, sorted_ws=sorted_xyz)          # [B,M]
+        self.points_sampled = ops.gather_point(xyz, self.kp_indices)          # [B,M,3]
+        self.knn_indices, _ = ops.knn_points(self.points_sampled, knn)        # [B,M,K]
         self.nn_dist, self.nn_idx = ops.three_nn(xyz, self.points_sampled, sorted1=sorted_xyz)   # [B,N,3] x2
 
 

@@ -7,6 +7,10 @@
 namespace dh3d {
 // knn.cu
 size_t knn_workspace_bytes(int B, int N);
+int knn_sort_launch(const float* pos, int B, int N, long long sb, int sp, int sd, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+int knn_query_sorted_launch(const void* workspace, int B, int N, int K, int32_t* ids, float* dists, cudaStream_t st);
+int fps_presorted_launch(int b, int n, int m, const void* knn_workspace, int32_t* out, cudaStream_t st);
 int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
                float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st);
 // fps.cu
@@ -248,6 +252,16 @@ int dh3d_conv_pointset_pm(const float* features_pm, const float* theta, const fl
                                  Dout, scale, shift, act, S(stream));
 }
 
+int dh3d_knn_sort_pm(const float* xyz_pm, int B, int N, void* workspace, size_t workspace_bytes, void* stream) {
+  return knn_sort_launch(xyz_pm, B, N, 3LL * N, 3, 1, workspace, workspace_bytes, S(stream));
+}
+int dh3d_knn_query_sorted(const void* workspace, int B, int N, int K, int32_t* ids, float* dists, void* stream) {
+  return knn_query_sorted_launch(workspace, B, N, K, ids, dists, S(stream));
+}
+int dh3d_farthest_point_sample_presorted(int b, int n, int m, const void* knn_workspace_of_inp, int32_t* out,
+                                         void* stream) {
+  return fps_presorted_launch(b, n, m, knn_workspace_of_inp, out, S(stream));
+}
 int dh3d_farthest_point_sample(int b, int n, int m, const float* inp, int32_t* out, void* stream) {
   return fps_launch(b, n, m, inp, out, S(stream));
 }

@@ -630,11 +630,12 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   }
 }
 
-int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
-               float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (!pos || !ids || !dists) return DH3D_ERR_NULL;
-  if (B <= 0 || N <= 0 || K <= 0) return DH3D_ERR_DIM;
-  if (K > 64 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
+// sort only: positions (any layout via strides) -> the workspace's cell-sorted copy + chunk boxes
+int knn_sort_launch(const float* pos, int B, int N, long long sb, int sp, int sd, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  if (!pos) return DH3D_ERR_NULL;
+  if (B <= 0 || N <= 0) return DH3D_ERR_DIM;
+  if (N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < knn_workspace_bytes(B, N)) return DH3D_ERR_WORKSPACE;
   if (((uintptr_t)workspace & 127) != 0) return DH3D_ERR_ALIGN;
   const KnnOrder o = knn_order(N);
@@ -642,8 +643,19 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   float4* sorted = reinterpret_cast<float4*>(workspace);
   float4* boxes = sorted + (size_t)B * Np;
   knn_sort_kernel<<<B, kSortThreads, 0, st>>>(pos, N, Np, sb, sp, sd, o.T, o.logT, o.logV, sorted, boxes);
-  int rc = launch_status();
-  if (rc != DH3D_OK) return rc;
+  return launch_status();
+}
+
+// query only: the workspace as knn_sort_launch (of the same B, N) left it
+int knn_query_sorted_launch(const void* workspace, int B, int N, int K, int32_t* ids, float* dists, cudaStream_t st) {
+  if (!workspace || !ids || !dists) return DH3D_ERR_NULL;
+  if (B <= 0 || N <= 0 || K <= 0) return DH3D_ERR_DIM;
+  if (K > 64 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
+  if (((uintptr_t)workspace & 127) != 0) return DH3D_ERR_ALIGN;
+  const KnnOrder o = knn_order(N);
+  const int Np = knn_padded(N);
+  const float4* sorted = reinterpret_cast<const float4*>(workspace);
+  const float4* boxes = sorted + (size_t)B * Np;
   dim3 grid(ceil_div(Np, kKnnThreads), B);
   const bool vec_ok = (((uintptr_t)ids | (uintptr_t)dists) & 15) == 0;
 #define DH3D_KNN(KC, EX)                                                                              \
@@ -660,6 +672,16 @@ int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int 
   else DH3D_KNN(64, false);   // keypoint NMS uses K = 50 (core/utils.py:17)
 #undef DH3D_KNN
   return launch_status();
+}
+
+int knn_launch(const float* pos, int B, int N, int K, long long sb, int sp, int sd, int32_t* ids,
+               float* dists, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!pos || !ids || !dists) return DH3D_ERR_NULL;
+  if (B <= 0 || N <= 0 || K <= 0) return DH3D_ERR_DIM;
+  if (K > 64 || N > 65536 || B > 65535) return DH3D_ERR_UNSUPPORTED;
+  int rc = knn_sort_launch(pos, B, N, sb, sp, sd, workspace, workspace_bytes, st);
+  if (rc != DH3D_OK) return rc;
+  return knn_query_sorted_launch(workspace, B, N, K, ids, dists, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -68,32 +68,36 @@ class DH3D(nn.Module):
         same_geometry = c.extract_global and c.gl_dilate == c.dilate
         cur = torch.cuda.current_stream(points.device)
 
-        # xyz-only geometry (FPS chain is latency-bound and independent of stage 1): side stream.  The side stream's
-        # 3-NN walks the cell-sorted copy of the cloud that the main stream's k-NN leaves in its workspace.
-        geometry, sorted_xyz, sorted_ready = None, None, None
+        # xyz-only geometry (FPS -> k-NN of the sampled points -> 3-NN) on a side stream next to stage 1.  The dense cloud
+        # is cell-sorted ONCE (knn_sort, first thing on the side stream): the main stream's k-NN query, the box-pruned FPS
+        # and the 3-NN all walk that copy.
+        geometry, sorted_xyz = None, None
+        own_knn = knn_inds is None
         if overlap:
             if self._side is None or self._side.device != points.device:
                 self._side = torch.cuda.Stream(device=points.device)
-            self._side.wait_stream(cur)     # (before the k-NN is enqueued: the side stream starts next to it)
-        if knn_inds is None:
-            knn_inds, _, sorted_xyz = ops.knn_points(points, c.knn_num, keep_workspace=True)
-            if overlap:
-                sorted_ready = torch.cuda.Event()
-                sorted_ready.record(cur)
-        if overlap:
+            self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
-                geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num, sorted_xyz, sorted_ready)
+                if own_knn:
+                    sorted_xyz = ops.knn_sort(points)
+                    sorted_ready = torch.cuda.Event()
+                    sorted_ready.record(self._side)
+                geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num, sorted_xyz)
                 # the main stream joins where the geometry is first consumed (stage 2's group_point), so the
                 # k-NN of the sampled points and the 3-NN run next to stage 1 instead of in front of it
                 geometry.ready = torch.cuda.Event()
                 geometry.ready.record(self._side)
+            if own_knn:
+                cur.wait_event(sorted_ready)
+                knn_inds, _ = ops.knn_query_sorted(sorted_xyz, c.knn_num)
             if not torch.cuda.is_current_stream_capturing():
                 for t in (geometry.kp_indices, geometry.points_sampled, geometry.knn_indices,
-                          geometry.nn_dist, geometry.nn_idx):
+                          geometry.nn_dist, geometry.nn_idx) + ((sorted_xyz,) if sorted_xyz is not None else ()):
                     t.record_stream(cur)
-                if sorted_xyz is not None:
-                    sorted_xyz.record_stream(self._side)
         else:
+            if own_knn:
+                sorted_xyz = ops.knn_sort(points)
+                knn_inds, _ = ops.knn_query_sorted(sorted_xyz, c.knn_num)
             geometry = DilateGeometry(points, points.shape[1] // c.dilate, c.knn_num, sorted_xyz)
 
         want = set(outputs)

@@ -37,6 +37,31 @@ def knn_points(xyz, k, keep_workspace=False):
     return ids, dists
 
 
+def knn_sort(xyz):
+    """xyz [B,N,3] -> the k-NN engine's workspace holding the cell-sorted copy of the cloud (+ chunk boxes): the input of
+    ``knn_query_sorted`` and of the ``sorted``-taking forms of ``farthest_point_sample`` / ``three_nn``."""
+    px = check(xyz, f32, "xyz", 3)
+    B, N, D = xyz.shape
+    if D != 3:
+        raise _lib.Dh3dError("knn_sort: last dim must be 3")
+    ws, wp, wn = workspace(query("dh3d_knn_workspace_bytes", B, N), xyz.device)
+    call("dh3d_knn_sort_pm", px, B, N, wp, wn, stream_ptr(xyz.device))
+    ws._dh3d_sorted_of = (B, N)
+    return ws
+
+
+def knn_query_sorted(sorted_ws, k):
+    """-> (ids [B,N,K] i32, dists [B,N,K] f32) of the cloud ``knn_sort`` sorted; knn_sort + this == knn_points."""
+    B, N = sorted_ws._dh3d_sorted_of
+    ids = torch.empty((B, N, k), dtype=i32, device=sorted_ws.device)
+    dists = torch.empty((B, N, k), dtype=f32, device=sorted_ws.device)
+    _lib.stats.tag = "B%d_N%d_K%d" % (B, N, k)
+    call("dh3d_knn_query_sorted", ctypes.c_void_p(sorted_ws.data_ptr()), B, N, int(k), check(ids, i32, "ids"),
+         check(dists, f32, "dists"), stream_ptr(sorted_ws.device))
+    _lib.stats.tag = None
+    return ids, dists
+
+
 def flex_conv(features, theta, bias, neighborhood, xyz, feature_bias=None, scale=None, shift=None,
               act=ACT_NONE):
     """features [B,N,Din], theta [3,Din,Dout], bias [Din,Dout], neighborhood [B,N,K] i32,
@@ -124,10 +149,19 @@ def conv_pointset(features, theta, bias, neighborhood, scale=None, shift=None, a
     return out
 
 
-def farthest_point_sample(npoint, inp):
+def farthest_point_sample(npoint, inp, sorted_ws=None):
+    """inp [B,N,3] -> [B,npoint] i32 (reference order and ties).  sorted_ws: the k-NN workspace of the same cloud
+    (``knn_sort`` / ``knn_points(keep_workspace=True)``), N <= 8192: the box-pruned kernel, same indices."""
     B, N, _ = inp.shape
     out = torch.empty((B, npoint), dtype=i32, device=inp.device)
     _lib.stats.tag = "B%d_N%d_M%d" % (B, N, int(npoint))
+    if sorted_ws is not None and N <= 8192:
+        if getattr(sorted_ws, "_dh3d_sorted_of", None) != (B, N):
+            raise _lib.Dh3dError("farthest_point_sample: sorted_ws is not the k-NN workspace of a [%d,%d,3] cloud" % (B, N))
+        call("dh3d_farthest_point_sample_presorted", B, N, int(npoint), ctypes.c_void_p(sorted_ws.data_ptr()),
+             check(out, i32, "out"), stream_ptr(inp.device))
+        _lib.stats.tag = None
+        return out
     call("dh3d_farthest_point_sample", B, N, int(npoint), check(inp, f32, "inp", 3),
          check(out, i32, "out"), stream_ptr(inp.device))
     _lib.stats.tag = None

@@ -64,6 +64,11 @@ DH3D_API int dh3d_knn_bruteforce(const float* positions_cm, int B, int Dp, int N
                         float* dists, void* workspace, size_t workspace_bytes, void* stream);
 DH3D_API int dh3d_knn_bruteforce_pm(const float* xyz_pm, int B, int N, int K, int32_t* ids, float* dists,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* dh3d_knn_bruteforce_pm in its two halves, for callers that share the cell-sorted copy of the cloud between ops
+ * (dh3d_farthest_point_sample_presorted, dh3d_three_nn_ws_presorted): sort xyz_pm [B,N,3] into the workspace
+ * (dh3d_knn_workspace_bytes(B, N)), then answer the K-NN query from it.  sort + query == dh3d_knn_bruteforce_pm. */
+DH3D_API int dh3d_knn_sort_pm(const float* xyz_pm, int B, int N, void* workspace, size_t workspace_bytes, void* stream);
+DH3D_API int dh3d_knn_query_sorted(const void* workspace, int B, int N, int K, int32_t* ids, float* dists, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FlexConv forward -- replaces op FlexConv
@@ -149,6 +154,13 @@ DH3D_API int dh3d_conv_pointset_pm(const float* features_pm, const float* theta,
  *   FPS: n <= 65536; the sample order reproduces the reference's 512-thread tie rule.
  * ------------------------------------------------------------------------------------------- */
 DH3D_API int dh3d_farthest_point_sample(int b, int n, int m, const float* inp, int32_t* out, void* stream);
+/* The same sampling on a cloud that is already cell-sorted: knn_workspace_of_inp = the workspace of a
+ * dh3d_knn_bruteforce_pm / dh3d_knn_sort_pm call on the same inp [b,n,3] (n <= 8192).  Identical indices in identical
+ * order (same distance arithmetic, same tie rule); a round only revisits the 32-point chunks whose bounding box can still
+ * hold a point whose running min-distance changes, so it is several times less work than the exhaustive rounds.
+ * DH3D's graph runs KnnBruteforce on the dense cloud before anything else (core/model.py:157), so the sort exists. */
+DH3D_API int dh3d_farthest_point_sample_presorted(int b, int n, int m, const void* knn_workspace_of_inp, int32_t* out,
+                                         void* stream);
 DH3D_API int dh3d_gather_point(int b, int n, int m, const float* inp, const int32_t* idx, float* out,
                       void* stream);
 DH3D_API int dh3d_group_point(int b, int n, int c, int m, int nsample, const float* points,

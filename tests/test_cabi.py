@@ -85,6 +85,10 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.dh3d_three_nn_ws_presorted(1, 64, 8, null, one, one, one, one, 1 << 30, null) == -1
     assert lib.dh3d_three_nn_ws_presorted(1, 64, 8, ctypes.c_void_p(256), one, one, one, ctypes.c_void_p(256), 16,
                                           null) == -4                                                   # workspace
+    assert lib.dh3d_farthest_point_sample_presorted(1, 64, 8, null, one, null) == -1
+    assert lib.dh3d_farthest_point_sample_presorted(1, 9000, 8, one, one, null) == -3                   # n > 8192
+    assert lib.dh3d_knn_sort_pm(one, 1, 64, ctypes.c_void_p(256), 16, null) == -4
+    assert lib.dh3d_knn_query_sorted(null, 1, 64, 8, one, one, null) == -1
     # chained two-layer entry: x, ldx, packed1, scale1, shift1, act1, packed2, scale2, shift2, act2, y, ldy, M, K1, N1, N2
     assert lib.dh3d_linear_chain_packed(one, 128, one, null, null, 1, one, null, null, 1, one, 256, 8, 128, 64, 256,
                                         null) == -3                                                     # N1 != 128

@@ -462,3 +462,55 @@ def test_three_nn_presorted_queries_bit_exact(B, n, m):
     assert torch.equal(i0, i2) and torch.equal(d0, d2)
     with pytest.raises(Exception):
         ops.three_nn(xyz1[:, :-1].contiguous(), xyz2, sorted1=ws)      # workspace of another shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,M", [(2, 8192, 1024), (3, 1000, 300), (1, 4097, 512), (2, 700, 700), (4, 8192, 64), (1, 33, 33)])
+def test_fps_presorted_bit_exact(B, N, M):
+    """dh3d_farthest_point_sample_presorted (box-pruned rounds on the k-NN engine's cell-sorted copy of the cloud) selects
+    the same points in the same order as the exhaustive kernel and as the oracle's restatement of the reference."""
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(N + M)
+    pts = make_cloud(rng, B, N, duplicates=N // 5)
+    d = cu(pts)
+    ws = ops.knn_sort(d)
+    a = ops.farthest_point_sample(M, d)
+    b = ops.farthest_point_sample(M, d, sorted_ws=ws)
+    assert torch.equal(a, b)
+    if N * M <= 8192 * 300:
+        assert np.array_equal(b.cpu().numpy(), oracle.farthest_point_sample(M, pts))
+
+
+@pytest.mark.gpu
+def test_fps_presorted_ties_degenerate_and_outlier_clouds():
+    """Lattice clouds (masses of equal distances: the (k mod 512, k) tie rule decides), an all-zero padding cloud, a cloud
+    with 1/8 of its points at 1e5 m (the reference's randsample=False padding) and the 1100-point tie case."""
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(14)
+    pts = lattice_cloud(rng, 4, 8192, step=1.0, side=6)
+    pts[1] = 0.0
+    pts[2] = make_cloud(rng, 1, 8192)[0]
+    pts[2, ::8] = 1.0e5
+    pts[3] = make_cloud(rng, 1, 8192, duplicates=6000)[0]
+    d = cu(pts)
+    for M in (2, 512, 1024):
+        a = ops.farthest_point_sample(M, d)
+        b = ops.farthest_point_sample(M, d, sorted_ws=ops.knn_sort(d))
+        assert torch.equal(a, b), M
+    tie = np.zeros((1, 1100, 3), np.float32)
+    tie[0, 1:] = 1.0
+    t = cu(tie)
+    assert ops.farthest_point_sample(2, t, sorted_ws=ops.knn_sort(t))[0, 1].item() == 512
+    with pytest.raises(Exception):
+        ops.farthest_point_sample(8, d[:, :100].contiguous(), sorted_ws=ops.knn_sort(d))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,K", [(2, 8192, 8), (3, 1000, 16), (1, 300, 50)])
+def test_knn_sort_plus_query_equals_knn_points(B, N, K):
+    from dh3d_b200 import ops
+    rng = np.random.RandomState(N + K)
+    d = cu(make_cloud(rng, B, N, duplicates=N // 7))
+    i0, d0 = ops.knn_points(d, K)
+    i1, d1 = ops.knn_query_sorted(ops.knn_sort(d), K)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1)

@@ -245,13 +245,14 @@ fps_smem_kernel(int n, int m, const float* __restrict__ dataset, int32_t* __rest
 //      the bound never exceeds the computed distance of a point inside) -- a chunk whose bound is not below its maximum
 //      cannot change and is skipped;
 //   2. re-reduces only the remaining chunks (one point per lane, REDUX.MAX on the distance bits + REDUX.MIN on the tie
-//      rank), chunks dealt round-robin to the 8 warps so that a spatial neighbourhood spreads over all of them;
-//   3. takes the arg-max over the 256 chunk maxima (warp REDUX, 8 shared-memory slots, ONE barrier per round).
+//      rank), chunks dealt round-robin to the 16 warps so that a spatial neighbourhood spreads over all of them;
+//   3. takes the arg-max over the 256 chunk maxima (warp REDUX, 16 shared-memory slots, ONE barrier per round).
 // Same result as the exhaustive scan, point for point: identical distance arithmetic on identical floats, and the
 // reference's tie order (smallest (k mod 512, k) among maximal d2, see the header of this file) carried as the rank tk.
-// One 256-thread CTA per cloud on 32 SMs instead of a 4-CTA cluster on 128: ~0.25 ms instead of 0.38 alone, and the
-// k-NN that runs next to it keeps most of the machine.
-constexpr int kFpsBThreads = 256;    // 8 warps (32 warps measured slower: the per-round barrier and reductions dominate)
+// One 512-thread CTA per cloud on 32 SMs instead of a 4-CTA cluster on 128.  Alone it is no faster than the exhaustive
+// kernel (0.38 vs 0.42 ms: a round revisits ~17 of 256 chunks, ~4 of them on the busiest warp, and pays one barrier and
+// six REDUX per round), but the k-NN that runs next to it keeps the other 116 SMs to itself.
+constexpr int kFpsBThreads = 512;    // 16 warps: 0.381 ms for 32 x 8192 -> 1024 (8 warps 0.399, 32 warps 0.446: barrier + reductions)
 constexpr int kFpsBChunk = 32;      // == kKnnChunk
 constexpr int kFpsBSuper = 16;      // == kKnnSuper
 
@@ -284,7 +285,7 @@ fps_bucket_kernel(int n, int np, int m, const float4* __restrict__ sorted, const
     stk[i] = valid ? (unsigned short)((k & 511) * V + (k >> 9)) : (unsigned short)0xFFFF;
     if (k == 0) s_first = i;
   }
-  // this lane's chunk (dealt round-robin: chunk c belongs to warp c % 32, lane c / 32 -- all 32 lanes at n = 8192)
+  // this lane's chunk (dealt round-robin: chunk c belongs to warp c % 16, lane c / 16 -- lanes 0..15 at n = 8192)
   constexpr int NW = kFpsBThreads / 32;
   const int c = lane * NW + warp;
   const bool own = c < nchunks;
@@ -323,7 +324,7 @@ fps_bucket_kernel(int n, int np, int m, const float4* __restrict__ sorted, const
       const unsigned kmin = __reduce_min_sync(0xffffffffu, bits == wmax ? key : 0xFFFFFFFFu);
       if (lane == l) { cmax = __int_as_float(wmax); ckey = kmin; }
     }
-    // arg-max over this warp's chunks, then over the 8 warps
+    // arg-max over this warp's chunks, then over the warps
     const int cb = __float_as_int(cmax);
     const int wmax = __reduce_max_sync(0xffffffffu, cb);
     const unsigned wkey = __reduce_min_sync(0xffffffffu, cb == wmax ? ckey : 0xFFFFFFFFu);

@@ -1,0 +1,18 @@
+#!/bin/bash
+timeout 300 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "fps" 2>&1 | tail -2
+timeout 120 python - <<PY
+import torch, sys
+sys.path.insert(0,'.')
+from dh3d_b200 import ops
+from bench import synth_clouds
+pts = synth_clouds(32, 8192, 0).cuda()
+ws = ops.knn_sort(pts)
+def t(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a,b=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/reps
+print('fps exhaustive %.4f ms  presorted %.4f ms' % (t(lambda: ops.farthest_point_sample(1024, pts)), t(lambda: ops.farthest_point_sample(1024, pts, sorted_ws=ws))))
+PY

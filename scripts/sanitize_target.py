@@ -32,6 +32,9 @@ nbr, _ = ops.knn_points(pts, 8)
 if want("fps"):
     ops.farthest_point_sample(256, pts)
     ops.farthest_point_sample(64, pts[:, :700].contiguous())
+    ops.farthest_point_sample(256, pts, sorted_ws=ops.knn_sort(pts))       # box-pruned kernel on the sorted cloud
+    z = torch.zeros((1, 1024, 3), device="cuda")
+    ops.farthest_point_sample(64, z, sorted_ws=ops.knn_sort(z))
     print("fps ok")
 if want("three_nn"):
     kp = ops.farthest_point_sample(256, pts)

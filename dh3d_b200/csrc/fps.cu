@@ -309,8 +309,9 @@ fps_bucket_kernel(int n, int np, int m, const float4* __restrict__ sorted, const
     // (round 1 visits every chunk that holds a point, whatever the bound: that is where the chunk maxima get their keys;
     //  !(lb >= cmax) rather than lb < cmax so that a NaN bound updates instead of skipping)
     unsigned mask = __ballot_sync(0xffffffffu, own && cmax >= 0.f && (j == 1 || !(lb >= cmax)));
-    while (mask) {   // (4 chunks per iteration with their REDUX chains interleaved measured slower: most iterations
-                     //  then repeat a chunk to fill the slots)
+    while (mask) {   // (measured slower: 4 chunks per iteration with interleaved REDUX chains -- most iterations then
+                     //  repeat a chunk to fill the slots, 0.46 ms; two chunks per iteration on half-warps with
+                     //  half-mask reductions, 0.72 ms)
       const int l = __ffs(mask) - 1;
       mask &= mask - 1u;
       const int i = (l * NW + warp) * kFpsBChunk + lane;

@@ -16,3 +16,9 @@ def t(fn, reps=10):
     b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/reps
 print('fps exhaustive %.4f ms  presorted %.4f ms' % (t(lambda: ops.farthest_point_sample(1024, pts)), t(lambda: ops.farthest_point_sample(1024, pts, sorted_ws=ws))))
 PY
+timeout 600 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-sensitivity --no-modes > gpurun_out/bench_r3o.json 2> gpurun_out/bench_r3o.err; echo "bench rc=$?"
+python - <<PY
+import json
+d=[json.loads(l) for l in open('gpurun_out/bench_r3o.json') if l.startswith('{')][0]
+print('value %.0f  ms/step %.4f e2e %.0f' % (d['value'], d['ms_per_step'], d['e2e']['value']))
+PY

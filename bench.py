@@ -186,13 +186,13 @@ def algorithmic(tag, name):
     if name == "dh3d_linear_join_packed":   # both inputs and weights once, y and its normalised copy once
         M, Ka, Kb, N = d["M"], d["Ka"], d["Kb"], d["N"]
         return 4.0 * (M * (Ka + Kb) + (Ka + Kb) * N + 2 * M * N), 2.0 * M * (Ka + Kb) * N, "hbm"
-    if name == "dh3d_knn_bruteforce_pm":
+    if name in ("dh3d_knn_bruteforce_pm", "dh3d_knn_query_sorted"):
         B, N, K = d["B"], d["N"], d["K"]
         return B * (12.0 * N + 8.0 * N * K), 8.0 * B * N * N, "alu"
     if name == "dh3d_netvlad":   # 4*[nD + n + 2*D*Kc + 256] per cloud + the hidden weights once
         B, N, D, Kc, O = d["B"], d["N"], d["D"], d["Kc"], d["O"]
         return 4.0 * (B * (N * D + N + O) + 2 * D * Kc + D * Kc * O), B * 4.0 * N * D * Kc, "hbm"
-    if name == "dh3d_farthest_point_sample":
+    if name in ("dh3d_farthest_point_sample", "dh3d_farthest_point_sample_presorted"):
         B, N, M = d["B"], d["N"], d["M"]
         return B * (12.0 * N + 4.0 * M), 8.0 * B * N * (M - 1), "latency"
     if name == "dh3d_flex_pool_pm":          # 4*[2nD + nD(argmax) + nK]
@@ -204,7 +204,7 @@ def algorithmic(tag, name):
     if name in ("dh3d_group_point", "dh3d_group_point_ld"):   # 4*[m*S*C*2 + m*S]
         B, M, S, C = d["B"], d["M"], d["S"], d["C"]
         return 4.0 * B * (2 * M * S * C + M * S), 0.0, "hbm"
-    if name == "dh3d_three_nn_ws":           # 12(n+m) + 24n
+    if name in ("dh3d_three_nn_ws", "dh3d_three_nn_ws_presorted"):           # 12(n+m) + 24n
         B, n, m = d["B"], d["n"], d["m"]
         return B * (12.0 * (n + m) + 24.0 * n), 8.0 * B * n * m, "alu"
     if name in ("dh3d_three_interpolate", "dh3d_three_interpolate_from_dist", "dh3d_three_interpolate_ld"):
@@ -222,7 +222,9 @@ OP_KERNEL = {
     "dh3d_linear_packed": ("gemm_tc16_kernel",),
     "dh3d_netvlad": ("netvlad_tc2_kernel", "netvlad_tc_kernel"),
     "dh3d_knn_bruteforce_pm": ("knn_query_kernel<8, 1, 1",),
+    "dh3d_knn_query_sorted": ("knn_query_kernel<8, 1, 1",),
     "dh3d_farthest_point_sample": ("fps_cluster_kernel",),
+    "dh3d_farthest_point_sample_presorted": ("fps_bucket_kernel",),
     "dh3d_flex_conv_pm": ("flexconv_ca_kernel",),
     "dh3d_flex_conv_pm_packed": ("flexconv_ca_kernel",),
     "dh3d_linear_join_packed": ("gemm_join16_kernel",),

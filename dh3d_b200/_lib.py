@@ -101,7 +101,7 @@ _KERNELS_PER_CALL = {
     "dh3d_flex_conv": 8,                                             # 4 transposes + 2 theta_ext + fold_bias + fused kernel
     "dh3d_flex_conv_pm": 4,                                          # 2 theta_ext forms + fold_bias + the fused kernel
     "dh3d_flex_conv_prepack": 3, "dh3d_flex_conv_pm_packed": 1,      # weights once; then the fused kernel only
-    "dh3d_query_ball_point": 2, "dh3d_netvlad": 3, "dh3d_three_nn_ws": 3, "dh3d_three_nn_ws_presorted": 2,   # netvlad: cluster-weight prepack + aggregate + tail
+    "dh3d_query_ball_point": 2, "dh3d_netvlad": 3, "dh3d_three_nn_ws": 3, "dh3d_three_nn_ws_presorted": 2,   # (knn_sort_pm / knn_query_sorted / fps_presorted: 1 each) netvlad: cluster-weight prepack + aggregate + tail
     "dh3d_flex_conv_grad_pm": 6, "dh3d_flex_conv_grad": 11, "dh3d_conv_pointset_grad": 5, "dh3d_flex_deconv": 7,
     "dh3d_keypoint_nms": 5,
 }

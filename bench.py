@@ -204,7 +204,7 @@ def algorithmic(tag, name):
     if name in ("dh3d_group_point", "dh3d_group_point_ld"):   # 4*[m*S*C*2 + m*S]
         B, M, S, C = d["B"], d["M"], d["S"], d["C"]
         return 4.0 * B * (2 * M * S * C + M * S), 0.0, "hbm"
-    if name in ("dh3d_three_nn_ws", "dh3d_three_nn_ws_presorted"):           # 12(n+m) + 24n
+    if name in ("dh3d_three_nn_ws", "dh3d_three_nn_ws_presorted", "dh3d_three_nn_presorted2"):           # 12(n+m) + 24n
         B, n, m = d["B"], d["n"], d["m"]
         return B * (12.0 * (n + m) + 24.0 * n), 8.0 * B * n * m, "alu"
     if name in ("dh3d_three_interpolate", "dh3d_three_interpolate_from_dist", "dh3d_three_interpolate_ld"):

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "dh3d_three_nn_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "dh3d_three_nn_ws": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _c_size_t, _p]),
     "dh3d_three_nn_ws_presorted": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p, _c_size_t, _p]),
+    "dh3d_three_nn_presorted2": (_c_int, [_c_int, _c_int, _c_int, _p, _p, _p, _p, _p]),
     "dh3d_three_interpolate": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_three_interpolate_from_dist": (_c_int, [_c_int] * 4 + [_p] * 5),
     "dh3d_linear": (_c_int, [_p, _c_int, _p, _p, _p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p]),

@@ -51,8 +51,9 @@ class DilateGeometry(object):
             torch.cuda.current_stream(xyz.device).wait_event(sorted_ready)
         self.kp_indices = ops.farthest_point_sample(npoint, xyz, sorted_ws=sorted_xyz)          # [B,M]
         self.points_sampled = ops.gather_point(xyz, self.kp_indices)          # [B,M,3]
-        self.knn_indices, _ = ops.knn_points(self.points_sampled, knn)        # [B,M,K]
-        self.nn_dist, self.nn_idx = ops.three_nn(xyz, self.points_sampled, sorted1=sorted_xyz)   # [B,N,3] x2
+        self.knn_indices, _, sorted_s = ops.knn_points(self.points_sampled, knn, keep_workspace=True)    # [B,M,K]
+        self.nn_dist, self.nn_idx = ops.three_nn(xyz, self.points_sampled, sorted1=sorted_xyz,
+                                                 sorted2=sorted_s if sorted_xyz is not None else None)   # [B,N,3] x2
 
 
 def subsample(points, feat, targetnum, kp_idx=None):

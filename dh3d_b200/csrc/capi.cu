@@ -39,6 +39,8 @@ int three_nn_launch(int b, int n, int m, const float* xyz1, const float* xyz2, f
 size_t three_nn_workspace_bytes(int b, int n, int m);
 int three_nn_presorted_launch(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2, float* dist,
                               int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int three_nn_presorted2_launch(int b, int n, int m, const void* knn_workspace_of_xyz1, const void* knn_workspace_of_xyz2,
+                               float* dist, int32_t* idx, cudaStream_t st);
 int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
                            int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int three_interpolate_launch(int b, int m, int c, int n, const float* points, const int32_t* idx,
@@ -285,6 +287,10 @@ int dh3d_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, flo
   return three_nn_launch(b, n, m, xyz1, xyz2, dist, idx, S(stream));
 }
 size_t dh3d_three_nn_workspace_bytes(int b, int n, int m) { return three_nn_workspace_bytes(b, n, m); }
+int dh3d_three_nn_presorted2(int b, int n, int m, const void* knn_workspace_of_xyz1, const void* knn_workspace_of_xyz2,
+                             float* dist, int32_t* idx, void* stream) {
+  return three_nn_presorted2_launch(b, n, m, knn_workspace_of_xyz1, knn_workspace_of_xyz2, dist, idx, S(stream));
+}
 int dh3d_three_nn_ws_presorted(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2, float* dist,
                                int32_t* idx, void* workspace, size_t workspace_bytes, void* stream) {
   return three_nn_presorted_launch(b, n, m, knn_workspace_of_xyz1, xyz2, dist, idx, workspace, workspace_bytes,

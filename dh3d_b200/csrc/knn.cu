@@ -308,13 +308,16 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
     float bmx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     const float4 q = out[c * kKnnChunk + lane];
     int mr = INT_MAX;   // smallest tie rank in the chunk: with the box bound, a lower bound of every packed (key, rank)
+    int mi = INT_MAX;   // smallest point index (the 3-NN metric's tie rank): one sorted copy serves both metrics
     if (__float_as_int(q.w) >= 0) {
       bmn[0] = q.x; bmx[0] = q.x;
       bmn[1] = q.y; bmx[1] = q.y;
       bmn[2] = q.z; bmx[2] = q.z;
       mr = knn_rank_of(__float_as_int(q.w), T, logT, logV);
+      mi = __float_as_int(q.w);
     }
     mr = __reduce_min_sync(0xffffffffu, mr);
+    mi = __reduce_min_sync(0xffffffffu, mi);
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -324,7 +327,7 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
       }
     if (lane == 0) {
       bx[2 * c] = make_float4(bmn[0], bmn[1], bmn[2], __int_as_float(mr));
-      bx[2 * c + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+      bx[2 * c + 1] = make_float4(bmx[0], bmx[1], bmx[2], __int_as_float(mi));
     }
   }
   __syncthreads();
@@ -333,12 +336,15 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
   for (int s = warp; s < nsuper; s += kSortThreads / 32) {
     const int c = s * kKnnSuper + (lane & (kKnnSuper - 1));
     float4 lo4 = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, __int_as_float(INT_MAX));
-    float4 hi4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, 0.f);
+    float4 hi4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, __int_as_float(INT_MAX));
     if (c < nchunks) { lo4 = bx[2 * c]; hi4 = bx[2 * c + 1]; }
     float bmn[3] = {lo4.x, lo4.y, lo4.z}, bmx[3] = {hi4.x, hi4.y, hi4.z};
-    int mr = __float_as_int(lo4.w);
+    int mr = __float_as_int(lo4.w), mi = __float_as_int(hi4.w);
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) mr = min(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+    for (int o = 8; o > 0; o >>= 1) {
+      mr = min(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+      mi = min(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -348,7 +354,7 @@ knn_sort_kernel(const float* __restrict__ pos, int N, int Np, long long sb, int 
       }
     if (lane == 0) {
       sbx[2 * s] = make_float4(bmn[0], bmn[1], bmn[2], __int_as_float(mr));
-      sbx[2 * s + 1] = make_float4(bmx[0], bmx[1], bmx[2], 0.f);
+      sbx[2 * s + 1] = make_float4(bmx[0], bmx[1], bmx[2], __int_as_float(mi));
     }
   }
 }
@@ -377,6 +383,7 @@ struct KnnMetric {      // knn_bruteforce_kernel_gpu.cu.cc:102-107 (nvcc-contrac
   static __device__ __forceinline__ int point_of(int r, int T, int logV) { return knn_point_of(r, T, logV); }
   static constexpr uint32_t kInitKey = 0x7f7fffffu;  // FLT_MAX, the reference's padding key
   static constexpr int kInitRank = INT_MAX;
+  static constexpr bool kRankIsIndex = false;   // boxes: smallest tie rank of the box in lo.w
 };
 struct ThreeNnMetric {  // tf_interpolate.cpp:60-103: un-fused (dx*dx + dy*dy) + dz*dz, key = d2, ties to low index
   static __device__ __forceinline__ float d2(float dx, float dy, float dz) {
@@ -391,6 +398,7 @@ struct ThreeNnMetric {  // tf_interpolate.cpp:60-103: un-fused (dx*dx + dy*dy) +
   static __device__ __forceinline__ int point_of(int r, int, int) { return r; }
   static constexpr uint32_t kInitKey = 0x7f800000u;  // best = 1e40 -> +inf in float, index 0
   static constexpr int kInitRank = 0;
+  static constexpr bool kRankIsIndex = true;    // boxes: smallest point index of the box in hi.w
 };
 
 
@@ -532,7 +540,9 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
   for (int sstep = 0; sstep <= 2 * sreach; ++sstep) {
     const int sc = (sstep & 1) ? s0 + ((sstep + 1) >> 1) : s0 - (sstep >> 1);
     if (sc < 0 || sc >= nsuper) continue;
-    if (!__any_sync(0xffffffffu, box_can_enter(box_lb(sbx, sc), __float_as_int(__ldg(sbx + 2 * sc).w)))) continue;
+    if (!__any_sync(0xffffffffu, box_can_enter(box_lb(sbx, sc),
+                                               __float_as_int(__ldg(sbx + 2 * sc + (M::kRankIsIndex ? 1 : 0)).w))))
+      continue;
     const int cbeg = sc * kKnnSuper, cend = min(cbeg + kKnnSuper, nchunks);
     const int cn = cend - cbeg;
     float4 blo = make_float4(0.f, 0.f, 0.f, 0.f), bhi = blo;
@@ -563,7 +573,7 @@ knn_query_kernel(const float4* __restrict__ qsorted, int Nq, int Nqp, const floa
                     lz = __shfl_sync(0xffffffffu, blo.z, j);
         const float hx = __shfl_sync(0xffffffffu, bhi.x, j), hy = __shfl_sync(0xffffffffu, bhi.y, j),
                     hz = __shfl_sync(0xffffffffu, bhi.z, j);
-        const int mr = __shfl_sync(0xffffffffu, __float_as_int(blo.w), j);
+        const int mr = __shfl_sync(0xffffffffu, __float_as_int(M::kRankIsIndex ? bhi.w : blo.w), j);
         const float ex = fmaxf(fmaxf(lx - qx, qx - hx), 0.f);
         const float ey = fmaxf(fmaxf(ly - qy, qy - hy), 0.f);
         const float ez = fmaxf(fmaxf(lz - qz, qz - hz), 0.f);
@@ -700,42 +710,59 @@ size_t three_nn_workspace_bytes(int b, int n, int m) {
 // (x,y,z,index) [b][knn_padded(n)], any cell order): the query sort is then skipped (DH3D runs the k-NN of the dense
 // cloud anyway; its sort is 30 us of the side stream's chain)
 static int three_nn_pruned_impl(int b, int n, int m, const float* xyz1, const float4* sorted1, const float* xyz2,
-                                float* dist, int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if ((!xyz1 && !sorted1) || !xyz2 || !dist || !idx) return DH3D_ERR_NULL;
+                                const float4* sorted2, float* dist, int32_t* idx, void* workspace,
+                                size_t workspace_bytes, cudaStream_t st) {
+  if ((!xyz1 && !sorted1) || (!xyz2 && !sorted2) || !dist || !idx) return DH3D_ERR_NULL;
   if (b <= 0 || n <= 0 || m <= 0) return DH3D_ERR_DIM;
   if (b > 65535) return DH3D_ERR_UNSUPPORTED;
-  if (!workspace || workspace_bytes < three_nn_workspace_bytes(b, n, m)) return DH3D_ERR_WORKSPACE;
-  if ((((uintptr_t)workspace | (uintptr_t)sorted1) & 127) != 0) return DH3D_ERR_ALIGN;
+  const bool need_ws = !sorted1 || !sorted2;
+  if (need_ws && (!workspace || workspace_bytes < three_nn_workspace_bytes(b, n, m))) return DH3D_ERR_WORKSPACE;
+  if ((((uintptr_t)workspace | (uintptr_t)sorted1 | (uintptr_t)sorted2) & 127) != 0) return DH3D_ERR_ALIGN;
   const int np1 = knn_padded(n), np2 = knn_padded(m);
   float4* cands = reinterpret_cast<float4*>(workspace);
   float4* boxes = cands + (size_t)b * np2;
   float4* queries = boxes + (size_t)b * knn_box_f4(np2);
   float4* qboxes = queries + (size_t)b * np1;
   int rc;
-  // tie rank of the 3-NN metric = the index itself (T = 2^30, V = 1)
+  // tie rank of the 3-NN metric = the index itself: the sort kernel leaves the smallest INDEX of every box in hi.w
+  // whatever rank parameters it ran with, so a k-NN workspace of the same points serves as well as an own sort
   if (!sorted1) {
     knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz1, n, np1, 3LL * n, 3, 1, 1 << 30, 30, 0, queries, qboxes);
     if ((rc = launch_status()) != DH3D_OK) return rc;
   }
-  knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, 1 << 30, 30, 0, cands, boxes);
-  rc = launch_status();
-  if (rc != DH3D_OK) return rc;
+  const float4* c_pts = cands;
+  const float4* c_box = boxes;
+  if (sorted2) {   // a k-NN workspace of xyz2: [b][np2] sorted points, then the boxes
+    c_pts = sorted2;
+    c_box = sorted2 + (size_t)b * np2;
+  } else {
+    knn_sort_kernel<<<b, kSortThreads, 0, st>>>(xyz2, m, np2, 3LL * m, 3, 1, 1 << 30, 30, 0, cands, boxes);
+    if ((rc = launch_status()) != DH3D_OK) return rc;
+  }
   dim3 grid(ceil_div(np1, kKnnThreads), b);
   knn_query_kernel<4, false, false, ThreeNnMetric><<<grid, kKnnThreads, 0, st>>>(
-      sorted1 ? sorted1 : queries, n, np1, cands, boxes, np2, 0, 0, 0, 3, idx, dist);
+      sorted1 ? sorted1 : queries, n, np1, c_pts, c_box, np2, 0, 0, 0, 3, idx, dist);
   return launch_status();
 }
 
 int three_nn_pruned_launch(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist,
                            int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  return three_nn_pruned_impl(b, n, m, xyz1, nullptr, xyz2, dist, idx, workspace, workspace_bytes, st);
+  return three_nn_pruned_impl(b, n, m, xyz1, nullptr, xyz2, nullptr, dist, idx, workspace, workspace_bytes, st);
 }
 
 int three_nn_presorted_launch(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2, float* dist,
                               int32_t* idx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (!knn_workspace_of_xyz1) return DH3D_ERR_NULL;
-  return three_nn_pruned_impl(b, n, m, nullptr, reinterpret_cast<const float4*>(knn_workspace_of_xyz1), xyz2, dist, idx,
-                              workspace, workspace_bytes, st);
+  return three_nn_pruned_impl(b, n, m, nullptr, reinterpret_cast<const float4*>(knn_workspace_of_xyz1), xyz2, nullptr,
+                              dist, idx, workspace, workspace_bytes, st);
+}
+
+// both clouds pre-sorted (k-NN workspaces of xyz1 and of xyz2): one launch, no workspace
+int three_nn_presorted2_launch(int b, int n, int m, const void* knn_workspace_of_xyz1, const void* knn_workspace_of_xyz2,
+                               float* dist, int32_t* idx, cudaStream_t st) {
+  if (!knn_workspace_of_xyz1 || !knn_workspace_of_xyz2) return DH3D_ERR_NULL;
+  return three_nn_pruned_impl(b, n, m, nullptr, reinterpret_cast<const float4*>(knn_workspace_of_xyz1), nullptr,
+                              reinterpret_cast<const float4*>(knn_workspace_of_xyz2), dist, idx, nullptr, 0, st);
 }
 
 }  // namespace dh3d

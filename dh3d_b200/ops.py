@@ -231,10 +231,11 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
-def three_nn(xyz1, xyz2, exhaustive=False, sorted1=None):
+def three_nn(xyz1, xyz2, exhaustive=False, sorted1=None, sorted2=None):
     """3 nearest xyz2 points of every xyz1 point (squared distances, reference arithmetic and ties).
     Default: Morton-sorted box-pruned scan (same results); exhaustive=True: the plain tiled scan.
-    sorted1: the workspace ``knn_points(xyz1, k, keep_workspace=True)`` returned (skips the sort of xyz1)."""
+    sorted1 / sorted2: the workspaces ``knn_sort`` / ``knn_points(..., keep_workspace=True)`` returned for xyz1 / xyz2
+    (skips sorting those points again; sorted2 needs sorted1)."""
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     dist = torch.empty((B, n, 3), dtype=f32, device=xyz1.device)
@@ -243,11 +244,19 @@ def three_nn(xyz1, xyz2, exhaustive=False, sorted1=None):
         call("dh3d_three_nn", B, n, m, check(xyz1, f32, "xyz1", 3), check(xyz2, f32, "xyz2", 3),
              check(dist, f32, "dist"), check(idx, i32, "idx"), stream_ptr(xyz1.device))
         return dist, idx
-    ws, wp, wn = workspace(query("dh3d_three_nn_workspace_bytes", B, n, m), xyz1.device)
     _lib.stats.tag = "B%d_n%d_m%d" % (B, n, m)
+    if sorted1 is not None and getattr(sorted1, "_dh3d_sorted_of", None) != (B, n):
+        raise _lib.Dh3dError("three_nn: sorted1 is not the k-NN workspace of a [%d,%d,3] cloud" % (B, n))
+    if sorted2 is not None and (sorted1 is None or getattr(sorted2, "_dh3d_sorted_of", None) != (B, m)):
+        raise _lib.Dh3dError("three_nn: sorted2 must be the k-NN workspace of a [%d,%d,3] cloud, next to sorted1" % (B, m))
+    if sorted2 is not None:
+        call("dh3d_three_nn_presorted2", B, n, m, ctypes.c_void_p(sorted1.data_ptr()),
+             ctypes.c_void_p(sorted2.data_ptr()), check(dist, f32, "dist"), check(idx, i32, "idx"),
+             stream_ptr(xyz1.device))
+        _lib.stats.tag = None
+        return dist, idx
+    ws, wp, wn = workspace(query("dh3d_three_nn_workspace_bytes", B, n, m), xyz1.device)
     if sorted1 is not None:
-        if getattr(sorted1, "_dh3d_sorted_of", None) != (B, n):
-            raise _lib.Dh3dError("three_nn: sorted1 is not the k-NN workspace of a [%d,%d,3] cloud" % (B, n))
         call("dh3d_three_nn_ws_presorted", B, n, m, ctypes.c_void_p(sorted1.data_ptr()), check(xyz2, f32, "xyz2", 3),
              check(dist, f32, "dist"), check(idx, i32, "idx"), wp, wn, stream_ptr(xyz1.device))
         _lib.stats.tag = None

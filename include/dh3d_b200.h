@@ -182,6 +182,10 @@ DH3D_API int dh3d_three_nn_ws(int b, int n, int m, const float* xyz1, const floa
  * results as dh3d_three_nn / dh3d_three_nn_ws; the workspace of THIS call as for dh3d_three_nn_ws. */
 DH3D_API int dh3d_three_nn_ws_presorted(int b, int n, int m, const void* knn_workspace_of_xyz1, const float* xyz2,
                                float* dist, int32_t* idx, void* workspace, size_t workspace_bytes, void* stream);
+/* ... and with BOTH clouds sorted (the k-NN workspaces of xyz1 [b,n,3] and of xyz2 [b,m,3]: DH3D also runs the k-NN of
+ * the sampled points before the interpolation, core/backbones.py:64-70): one launch, no workspace. */
+DH3D_API int dh3d_three_nn_presorted2(int b, int n, int m, const void* knn_workspace_of_xyz1,
+                             const void* knn_workspace_of_xyz2, float* dist, int32_t* idx, void* stream);
 DH3D_API int dh3d_three_interpolate(int b, int m, int c, int n, const float* points, const int32_t* idx,
                            const float* weight, float* out, void* stream);
 /* fused caller-side step of core/backbones.py:91-96: weight = (1/max(d,1e-10))/sum(...) computed

@@ -42,6 +42,7 @@ if want("three_nn"):
     d, i = ops.three_nn(pts, m)
     _, _, ws = ops.knn_points(pts, 8, keep_workspace=True)
     ops.three_nn(pts, m, sorted1=ws)                    # query sort taken from the k-NN workspace
+    ops.three_nn(pts, m, sorted1=ws, sorted2=ops.knn_sort(m))
     ops.three_interpolate(rnd(2, 256, 128), i, d, weight_is_dist2=True)
     print("three_nn ok")
 if want("flexconv"):

@@ -85,6 +85,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.dh3d_three_nn_ws_presorted(1, 64, 8, null, one, one, one, one, 1 << 30, null) == -1
     assert lib.dh3d_three_nn_ws_presorted(1, 64, 8, ctypes.c_void_p(256), one, one, one, ctypes.c_void_p(256), 16,
                                           null) == -4                                                   # workspace
+    assert lib.dh3d_three_nn_presorted2(1, 64, 8, ctypes.c_void_p(256), null, one, one, null) == -1
     assert lib.dh3d_farthest_point_sample_presorted(1, 64, 8, null, one, null) == -1
     assert lib.dh3d_farthest_point_sample_presorted(1, 9000, 8, one, one, null) == -3                   # n > 8192
     assert lib.dh3d_knn_sort_pm(one, 1, 64, ctypes.c_void_p(256), 16, null) == -4

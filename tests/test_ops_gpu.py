@@ -460,6 +460,14 @@ def test_three_nn_presorted_queries_bit_exact(B, n, m):
     d2, i2 = ops.three_nn(xyz1, xyz2, sorted1=ws)
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
     assert torch.equal(i0, i2) and torch.equal(d0, d2)
+    # both clouds from k-NN workspaces (the candidates' boxes carry the smallest index next to the k-NN tie rank)
+    _, _, ws2 = ops.knn_points(xyz2, min(8, m), keep_workspace=True)
+    d3, i3 = ops.three_nn(xyz1, xyz2, sorted1=ws, sorted2=ws2)
+    assert torch.equal(i0, i3) and torch.equal(d0, d3)
+    z1, z2 = torch.zeros_like(xyz1), torch.zeros_like(xyz2)          # all-zero padding clouds: every distance ties
+    dz0, iz0 = ops.three_nn(z1, z2, exhaustive=True)
+    dz3, iz3 = ops.three_nn(z1, z2, sorted1=ops.knn_sort(z1), sorted2=ops.knn_sort(z2))
+    assert torch.equal(iz0, iz3) and torch.equal(dz0, dz3)
     with pytest.raises(Exception):
         ops.three_nn(xyz1[:, :-1].contiguous(), xyz2, sorted1=ws)      # workspace of another shape
 

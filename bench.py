@@ -706,15 +706,47 @@ def run_forward_workload(args):
             desc_keep[j * B:(j + 1) * B].copy_(out["globaldesc"], non_blocking=True)
         return out
 
-    def timed_region(i):
-        step(i)
-        if i == K - 1 and desc_keep is not None and world > 1:
+    # Two steps in flight: graph instance k replays on its own stream ("lane" k), so step i + 1 (other instance, other
+    # static buffers) starts next to step i and its latency-bound geometry kernels run under step i's tensor-bound
+    # heads (measured: 2.066 -> 1.965 ms per step, profiles/inflight_priority_r3r.txt; a third lane loses again).
+    # Steps stay whole and ordered per lane; the timed region ends when BOTH lanes have drained.
+    cur = torch.cuda.current_stream(dev)
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if graphs is not None and args.in_flight == 2 else None
+
+    def lane_step(i):
+        if lanes is None:
+            return step(i)
+        with torch.cuda.stream(lanes[i % 2]):
+            return step(i)
+
+    def fork_lanes():
+        for s in lanes or ():
+            s.wait_stream(cur)
+
+    def join_lanes():
+        for s in lanes or ():
+            cur.wait_stream(s)
+
+    def pipelined(n, tail=None):
+        """fn(i) for ctx.timed: n steps over the lanes, all lanes joined into the current stream (where ctx.timed
+        records its closing event) after the last one, then ``tail``."""
+        def fn(i):
+            if i == 0:
+                fork_lanes()
+            lane_step(i)
+            if i == n - 1:
+                join_lanes()
+                if tail is not None:
+                    tail()
+        return fn
+
+    def gather_tail():
+        if desc_keep is not None and world > 1:
             all_gather_descriptors(desc_keep)      # [K*B*world, 256] on every rank: the run's one collective
 
+    warm = pipelined(args.warmup, gather_tail)     # same issue pattern as the timed region; NCCL communicator warm
     for i in range(args.warmup):
-        step(i)
-    if desc_keep is not None and world > 1:
-        all_gather_descriptors(desc_keep)          # NCCL communicator / buffers warm
+        warm(i)
     ctx.barrier()
 
     # ---- per-op table (untimed pass, all C-ABI calls bracketed by events) -------------------------
@@ -743,10 +775,17 @@ def run_forward_workload(args):
     # ---- timed region: exactly K steps, inputs resident, the all-gather at its end ----------------
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
-    elapsed_ms = ctx.timed(timed_region, K)
+    elapsed_ms = ctx.timed(pipelined(K, gather_tail), K)
     clocks = sampler.stop()
     value = world * B * K / (elapsed_ms / 1e3)
     ms_per_step = elapsed_ms / K
+    # the same K steps strictly one after the other on one stream (= the latency of one step)
+    serial = None
+    if lanes is not None:
+        ms1 = ctx.timed(lambda i: step(i), K)
+        serial = {"ms_per_step": ms1 / K, "value": world * B * K / (ms1 / 1e3), "unit": "clouds/s",
+                  "what": "one step in flight: every replay on one stream (no all-gather); ms_per_step here is a "
+                          "step's latency, the headline's is elapsed / steps with two steps in flight"}
 
     # ---- dominant launch group, timed live with CUDA events in an eager pass over the same steps ---
     _lib.stats.reset()
@@ -763,7 +802,7 @@ def run_forward_workload(args):
         n_sus = max(K, int(math.ceil(args.sustained_s * 1e3 / ms_per_step)))
         s2 = ClockSampler(ctx.local_rank)
         s2.start()
-        ms = ctx.timed(lambda i: step(i), n_sus)
+        ms = ctx.timed(pipelined(n_sus), n_sus)
         c2 = s2.stop()
         sustained = {"seconds": ms / 1e3, "steps": n_sus, "value": world * B * n_sus / (ms / 1e3), "unit": "clouds/s",
                      "ms_per_step": ms / n_sus, "clocks": c2}
@@ -848,7 +887,9 @@ def run_forward_workload(args):
                    "parallelism": ("clouds sharded by rank, no data-path collective; ONE all_gather of the ranks' "
                                    "[steps*B,256] global descriptors at the end of the timed region")
                    if world > 1 else "single GPU",
-                   "launch": graph_note,
+                   "launch": graph_note + ("; two steps in flight (graph instance k on its own stream)"
+                                           if lanes is not None else ""),
+                   "steps_in_flight": 2 if lanes is not None else 1,
                    "l2": "inputs rotate over %d resident batches; one step streams > 1 GB of activations "
                          "through the 126 MB L2, so nothing survives between steps" % R},
         "e2e": e2e,
@@ -860,6 +901,7 @@ def run_forward_workload(args):
         "step_hbm": step_hbm,
         "op_roofline": op_rows,
         "sustained": sustained,
+        "one_step_in_flight": serial,
         "cpu_baseline": cpu,
         "ref_cuda": ref_cuda,
         "data_sensitivity": sens,
@@ -894,6 +936,9 @@ def run_retrieval_workload(args):
     host_batches = [host_all[i * B:(i + 1) * B] for i in range(K)]
     dev_batches = [dev_all[i * B:(i + 1) * B] for i in range(K)]
     R = K
+    _lib.stats.reset()
+    model(dev_batches[0], outputs=("globaldesc",))          # one eager forward: the kernels a graph replay launches
+    kernels_per_replay = _lib.stats.kernels
     graphs = [GraphedForward(model, dev_batches[0], outputs=("globaldesc",)) for _ in range(2)]
     desc = torch.empty((n_local, cfg.output_dim), dtype=torch.float32, device=dev)
     topk_host = torch.empty((n_local, 25), dtype=torch.int32).pin_memory()
@@ -905,18 +950,40 @@ def run_retrieval_workload(args):
         state["idx"] = idx
         return idx
 
-    def step_resident(i):
+    def fwd_resident(i):
         out = graphs[i % 2](dev_batches[i % R])
         desc[i * B:(i + 1) * B].copy_(out["globaldesc"], non_blocking=True)
-        if i == K - 1:
-            finish()
 
-    def step_e2e(i):
+    def fwd_e2e(i):
         pts = host_batches[i % R].to(dev, non_blocking=True)    # H2D of this micro-batch
         out = graphs[i % 2](pts)
         desc[i * B:(i + 1) * B].copy_(out["globaldesc"], non_blocking=True)
-        if i == K - 1:
-            topk_host.copy_(finish(), non_blocking=True)        # the job's result: [n_local, 25] neighbour ids
+
+    # two micro-batches in flight: graph instance k replays on its own stream (see run_forward_workload); the job's tail
+    # (all-gather + retrieval) runs on the current stream once both lanes have drained
+    cur = torch.cuda.current_stream(dev)
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if args.in_flight == 2 else None
+
+    def laned(fwd, tail):
+        def fn(i):
+            if lanes is None:
+                fwd(i)
+            else:
+                if i == 0:
+                    for s in lanes:
+                        s.wait_stream(cur)
+                with torch.cuda.stream(lanes[i % 2]):
+                    fwd(i)
+                if i == K - 1:
+                    for s in lanes:
+                        cur.wait_stream(s)
+            if i == K - 1:
+                tail()
+        return fn
+
+    step_resident = laned(fwd_resident, finish)
+    # the job's result: [n_local, 25] neighbour ids
+    step_e2e = laned(fwd_e2e, lambda: topk_host.copy_(finish(), non_blocking=True))
 
     for i in range(max(args.warmup, 3)):
         graphs[i % 2](dev_batches[i % R])
@@ -927,7 +994,7 @@ def run_retrieval_workload(args):
     sampler.start()
     ms = ctx.timed(step_resident, K)
     clocks = sampler.stop()
-    kernels = _lib.stats.kernels
+    kernels = _lib.stats.kernels + kernels_per_replay * K    # eager C-ABI calls (top-k) + K graph replays
     value = total / (ms / 1e3)
     ms_e2e = ctx.timed(step_e2e, K)
     e2e_value = total / (ms_e2e / 1e3)
@@ -947,7 +1014,9 @@ def run_retrieval_workload(args):
                    "clouds_per_gpu": n_local, "micro_batch": B, "outputs": "globaldesc only",
                    "parallelism": "contiguous shards of clouds per rank, no data-path collective; one all_gather_into_tensor "
                                   "of [%d,256] per rank (%d KiB) then dh3d_topk_l2 k=25" % (n_local, n_local),
-                   "launch": "forward replayed from a CUDA graph", "retrieval_self_match_first": self_first},
+                   "launch": "forward replayed from a CUDA graph" + ("; two micro-batches in flight (graph instance k on "
+                                                                      "its own stream)" if lanes is not None else ""),
+                   "steps_in_flight": 2 if lanes is not None else 1, "retrieval_self_match_first": self_first},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": B * N_POINTS * 12,
                 "d2h_bytes_per_step": n_local * 25 * 4 / K, "ms_total": ms_e2e,
                 "note": "per micro-batch: H2D of 32 clouds from pinned memory + forward; at the end one all-gather of the "
@@ -1044,6 +1113,8 @@ def main():
     ap.add_argument("--no-sensitivity", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2],
+                    help="steps in flight on the device (2 = the two graph instances replay on their own streams)")
     ap.add_argument("--op-table", default=None, help="write the per-op device-time table (JSON) here")
     args = ap.parse_args()
     if args.batch is None:

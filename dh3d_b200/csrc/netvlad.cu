@@ -37,7 +37,8 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
                          float* __restrict__ part_s, unsigned int* zero_word) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VladSmem& sm = *reinterpret_cast<VladSmem*>(smem_raw);
-  if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *zero_word = 0u;   // tail barrier counter
+  if (zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)   // the tail kernel's four counters
+    *reinterpret_cast<uint4*>(zero_word) = make_uint4(0u, 0u, 0u, 0u);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, slab = blockIdx.x;
   const int per = (N + slabs - 1) / slabs;
@@ -137,16 +138,28 @@ netvlad_aggregate_kernel(const float* __restrict__ feat, const float* __restrict
 }
 
 // ---- tail: slab combine + intra-norm -> 16384 x 256 projection -> BN / context gating / l2-norm, ONE launch ------------
-// Three phases of one persistent kernel (was three launches: 17 + 31 + 33 us for 32 clouds, each mostly launch ramp and
-// load latency), separated by grid barriers on a counter in the workspace (every CTA is resident: grid <= SM count,
-// one 256-thread CTA each).  Data written in one phase is read in the next with plain (coherent) loads.
-constexpr int kVQ = 8;     // clusters per phase-A work item: B * 8 items = one per CTA at B = 32
+// Three phases in ONE launch (was three launches: 17 + 31 + 33 us for 32 clouds, each mostly launch ramp and load
+// latency).  One CTA per work item; a CTA takes a TICKET (atomic counter) when it starts and the ticket names its item:
+// tickets [0, nA) are phase-A items, [nA, nA + nB) phase B, the rest phase C.  A later phase waits on a completion
+// counter of the phase before it.  A CTA therefore only ever waits for CTAs with LOWER tickets, i.e. CTAs that have
+// already started (resident or finished) and that wait, in turn, only for still lower tickets: progress never depends on
+// a CTA that has not been scheduled yet.  That holds with any number of these launches (or anything else) running
+// next to each other on other streams, unlike a spinning grid barrier, which deadlocks as soon as two half-resident
+// grids hold each other's SM slots.  Data written in one phase is read in the next with plain (coherent) loads.
+// Counters (workspace, zeroed by the aggregate kernel one launch ahead): [0] ticket, [1] phase-A items done,
+// [2] phase-B items done, [3] phase-C items done.
+constexpr int kVQ = 8;     // clusters per phase-A work item: B * 8 items
 
-__device__ __forceinline__ void nv_grid_barrier(unsigned int* ctr, unsigned int target) {
+__device__ __forceinline__ void nv_signal(unsigned int* ctr) {   // whole CTA: its item's stores are done
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(ctr, 1u);
+  }
+}
+
+__device__ __forceinline__ void nv_wait(const unsigned int* ctr, unsigned int target) {   // whole CTA
+  if (threadIdx.x == 0) {
     unsigned int v;
     do {   // relaxed polls (an acquire load costs a cache invalidation per poll), one fence once the count is in
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -213,7 +226,8 @@ __device__ __forceinline__ void nv_finalize_item(int b, int q, const float* __re
 // phase B, work item (slice, b0): split-K projection, rows [slice*64, slice*64+64) of hidden1_weights [16384, 256]
 // for the clouds b0 .. b0+31; thread = output column.  part_h [slices][B][256].
 __device__ __forceinline__ void nv_project_item(int slice, int b0, const float* vlad, const float* __restrict__ hw,
-                                                int B, int KD, float* part_h) {
+                                                int B, int KD, float* part_h, const unsigned int* done_a,
+                                                unsigned int n_a) {
   __shared__ __align__(16) float s_x[32][kVSlice];
   const int tid = threadIdx.x;
   const int nb = min(32, B - b0);
@@ -223,7 +237,7 @@ __device__ __forceinline__ void nv_project_item(int slice, int b0, const float* 
   float wv[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) wv[j] = __ldg(w + (long long)j * kVD);
-  __syncthreads();   // the previous item's readers of s_x are done
+  nv_wait(done_a, n_a);   // every phase-A item (the vlad rows of all clouds) is written; the weight loads are in flight
   for (int i = tid; i < 32 * kVSlice; i += kVD) {
     const int bb = i / kVSlice, r = i % kVSlice;
     s_x[bb][r] = bb < nb ? vlad[(long long)(b0 + bb) * KD + (long long)slice * kVSlice + r] : 0.f;   // written in phase A
@@ -312,34 +326,40 @@ struct NvTailArgs {
   const float* hw; float* part_h;
   const float* bn_scale; const float* bn_shift; const float* gw; const float* g_scale; const float* g_shift;
   int final_l2norm; float* out; int B;
-  unsigned int* barrier;   // zero at launch; the last CTA to leave zeroes it again
+  unsigned int* barrier;   // four counters (ticket, A / B / C items done): zero at launch, left zero by the last item
 };
 
 __global__ void __launch_bounds__(kVD)
 netvlad_tail_kernel(const NvTailArgs a) {
-  const int G = (int)gridDim.x;
-  for (int w = blockIdx.x; w < a.B * (kVK / kVQ); w += G)
-    nv_finalize_item(w / (kVK / kVQ), w % (kVK / kVQ), a.part_v, a.part_s, a.slabs, a.cw2, a.vlad, a.coln);
-  nv_grid_barrier(a.barrier, (unsigned)G);
-  const int slices = kVD * kVK / kVSlice;
-  const int groups = (a.B + 31) / 32;
-  for (int w = blockIdx.x; w < slices * groups; w += G)
-    nv_project_item(w % slices, (w / slices) * 32, a.vlad, a.hw, a.B, kVD * kVK, a.part_h);
-  nv_grid_barrier(a.barrier, 2u * (unsigned)G);
-  for (int b = blockIdx.x; b < a.B; b += G)
-    nv_head_item(b, a.part_h, slices, a.B, a.coln, a.bn_scale, a.bn_shift, a.gw, a.g_scale, a.g_shift,
-                 a.final_l2norm, a.out);
+  __shared__ unsigned int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.barrier, 1u);
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(a.barrier, 1u) == 3u * (unsigned)G - 1u) *a.barrier = 0u;
+  const unsigned int t = s_ticket;
+  const int slices = kVD * kVK / kVSlice;
+  const unsigned int n_a = (unsigned)a.B * (kVK / kVQ);
+  const unsigned int n_b = (unsigned)slices * (unsigned)((a.B + 31) / 32);
+  const unsigned int n_c = (unsigned)a.B;
+  if (t < n_a) {
+    nv_finalize_item((int)t / (kVK / kVQ), (int)t % (kVK / kVQ), a.part_v, a.part_s, a.slabs, a.cw2, a.vlad, a.coln);
+    nv_signal(a.barrier + 1);
+  } else if (t < n_a + n_b) {
+    const int w = (int)(t - n_a);
+    nv_project_item(w % slices, (w / slices) * 32, a.vlad, a.hw, a.B, kVD * kVK, a.part_h, a.barrier + 1, n_a);
+    nv_signal(a.barrier + 2);
+  } else if (t < n_a + n_b + n_c) {
+    nv_wait(a.barrier + 2, n_b);
+    nv_head_item((int)(t - n_a - n_b), a.part_h, slices, a.B, a.coln, a.bn_scale, a.bn_shift, a.gw, a.g_scale,
+                 a.g_shift, a.final_l2norm, a.out);
+    __syncthreads();
+    // the last item to finish leaves the counters zero again (nobody reads them any more: every other CTA is past its wait)
+    if (threadIdx.x == 0 && atomicAdd(a.barrier + 3, 1u) == n_c - 1u)
+      *reinterpret_cast<uint4*>(a.barrier) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 static int netvlad_tail_launch(const NvTailArgs& a, cudaStream_t st) {
-  int dev = 0, sms = kNumSMs;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int work = max(a.B * (kVK / kVQ), kVD * kVK / kVSlice);
-  // every CTA resident at once (the barriers spin): two 256-thread CTAs per SM (91 registers, 11 KB each), so that
-  // the projection's 256 weight slices are all in flight together
-  const int grid = work < 2 * sms ? work : 2 * sms;
+  const int slices = kVD * kVK / kVSlice;
+  const int grid = a.B * (kVK / kVQ) + slices * ((a.B + 31) / 32) + a.B;   // one CTA per work item of the three phases
   netvlad_tail_kernel<<<grid, kVD, 0, st>>>(a);
   return launch_status();
 }
@@ -390,7 +410,7 @@ int netvlad_launch(const float* features, const float* att, int B, int N, int D,
   float* part_h = reinterpret_cast<float*>(p); p += nv_part_h_bytes(B);
   unsigned int* barrier = reinterpret_cast<unsigned int*>(p); p += nv_barrier_bytes();
   void* tc_ws = p;
-  // (the tail kernel's grid-barrier counter: the workspace is not assumed to be zeroed, the aggregate kernel zeroes it)
+  // (the tail kernel's counters: the workspace is not assumed to be zeroed, the aggregate kernel zeroes them)
   NvTailArgs tail{part_v, part_s, 0, cw2, vlad, coln, hw, part_h, bn_scale, bn_shift, gw, gbn_scale, gbn_shift,
                   final_l2norm, out, B, barrier};
 

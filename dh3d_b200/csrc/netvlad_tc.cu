@@ -46,7 +46,7 @@ struct NvArgs {
   float* part_v;           // [B][P][256][64]
   float* part_s;           // [B][P][64]
   int N, tiles_per_cta, subslabs, P;
-  unsigned int* zero_word;   // the tail kernel's grid-barrier counter: zeroed here, one launch ahead of its use
+  unsigned int* zero_word;   // the tail kernel's four counters (16-byte aligned): zeroed here, one launch ahead of their use
 };
 
 // MN-major, 128B-swizzled operand: 128-byte rows of 64 fp16 along M; 8-row K groups 1024 B apart;
@@ -132,7 +132,8 @@ netvlad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                    const __grid_constant__ CUtensorMap tmWl, const NvArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  if (a.zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.zero_word = 0u;
+  if (a.zero_word && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    *reinterpret_cast<uint4*>(a.zero_word) = make_uint4(0u, 0u, 0u, 0u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NvSmem2::bars);
   uint64_t* raw_full = bars;         // [2] count 1 + tx: a whole raw tile landed in buffer b
   uint64_t* x_full = bars + 2;       // [2] count 128: buffer b converted to xh/xl

@@ -421,6 +421,45 @@ def test_netvlad_tiny_and_huge_feature_norms():
     close(out, net.netvlad(feat, att, p, final_l2norm=True))
 
 
+def test_netvlad_more_than_32_clouds():
+    """B > 32: two projection groups in the tail (phase-B items of both groups wait for every phase-A item)."""
+    from dh3d_b200.backbones import GlobalNetVLADBlock
+    from dh3d_b200.model import init_random_
+    from oracle import net
+    blk = init_random_(GlobalNetVLADBlock(), seed=11)
+    p = {"netvlad." + k: v.detach().numpy() for k, v in blk.named_parameters()}
+    blk = blk.cuda()
+    rng = np.random.RandomState(40)
+    feat = np.maximum(rng.randn(40, 96, 256), 0).astype(np.float32)
+    att = rng.rand(40, 96, 1).astype(np.float32)
+    close(blk(None, cu(feat), cu(att), final_l2norm=True), net.netvlad(feat, att, p, final_l2norm=True))
+
+
+@pytest.mark.timeout(120)
+def test_netvlad_calls_on_concurrent_streams_complete_and_agree():
+    """The tail's three phases hand over through counters inside one launch.  CTAs take tickets and only wait for lower
+    tickets, so any number of calls may overlap on other streams (a spinning grid barrier would deadlock here: four
+    544-CTA launches over-subscribe the machine's resident slots).  Results: bit-identical to the serial calls."""
+    from dh3d_b200.backbones import GlobalNetVLADBlock
+    from dh3d_b200.model import init_random_
+    blk = init_random_(GlobalNetVLADBlock(), seed=13).cuda()
+    rng = np.random.RandomState(3)
+    feats = [cu(np.maximum(rng.randn(32, 256, 256), 0).astype(np.float32)) for _ in range(4)]
+    atts = [cu(rng.rand(32, 256, 1).astype(np.float32)) for _ in range(4)]
+    want = [blk(None, f, a, final_l2norm=True).clone() for f, a in zip(feats, atts)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    got = [[] for _ in range(4)]
+    for rep in range(25):
+        for k, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                got[k].append(blk(None, feats[k], atts[k], final_l2norm=True))
+    torch.cuda.synchronize()
+    for k in range(4):
+        for g in got[k]:
+            assert torch.equal(g, want[k])
+
+
 # ------------------------------------------------------------------------ fused concat / add+l2norm
 def test_strided_group_interp_and_add_l2norm_are_bit_identical_to_the_unfused_ops():
     from dh3d_b200 import ops

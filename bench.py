@@ -669,7 +669,7 @@ def dominant_roofline(peaks, dominant, tot_ms, calls):
 def run_forward_workload(args):
     from dh3d_b200 import _lib
     from dh3d_b200.dist import all_gather_descriptors
-    from dh3d_b200.model import DH3D, GraphedForward, init_random_
+    from dh3d_b200.model import DH3D, GraphedForward, InFlightForward, init_random_
     ctx = Ctx(args)
     torch, dev, world, rank = ctx.torch, ctx.dev, ctx.world, ctx.rank
     cfg = workload_config(args)
@@ -706,36 +706,29 @@ def run_forward_workload(args):
             desc_keep[j * B:(j + 1) * B].copy_(out["globaldesc"], non_blocking=True)
         return out
 
-    # Two steps in flight: graph instance k replays on its own stream ("lane" k), so step i + 1 (other instance, other
-    # static buffers) starts next to step i and its latency-bound geometry kernels run under step i's tensor-bound
-    # heads (measured: 2.066 -> 1.965 ms per step, profiles/inflight_priority_r3r.txt; a third lane loses again).
+    # Two steps in flight (model.InFlightForward): graph instance k replays on its own stream ("lane" k), so step i + 1
+    # (other instance, other static buffers) starts next to step i and its latency-bound geometry kernels run under
+    # step i's tensor-bound heads (2.09 -> 1.94 ms per step, profiles/inflight_r3s.txt; a third lane loses again).
     # Steps stay whole and ordered per lane; the timed region ends when BOTH lanes have drained.
-    cur = torch.cuda.current_stream(dev)
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if graphs is not None and args.in_flight == 2 else None
+    inflight = InFlightForward(graphs) if graphs is not None and args.in_flight == 2 else None
 
     def lane_step(i):
-        if lanes is None:
+        if inflight is None:
             return step(i)
-        with torch.cuda.stream(lanes[i % 2]):
-            return step(i)
-
-    def fork_lanes():
-        for s in lanes or ():
-            s.wait_stream(cur)
-
-    def join_lanes():
-        for s in lanes or ():
-            cur.wait_stream(s)
+        keep = None
+        if desc_keep is not None:
+            j = i % max(K, 1)
+            keep = lambda out: desc_keep[j * B:(j + 1) * B].copy_(out["globaldesc"], non_blocking=True)  # noqa: E731
+        return inflight.submit(dev_batches[i % R], consume=keep)[0]
 
     def pipelined(n, tail=None):
         """fn(i) for ctx.timed: n steps over the lanes, all lanes joined into the current stream (where ctx.timed
         records its closing event) after the last one, then ``tail``."""
         def fn(i):
-            if i == 0:
-                fork_lanes()
             lane_step(i)
             if i == n - 1:
-                join_lanes()
+                if inflight is not None:
+                    inflight.join()
                 if tail is not None:
                     tail()
         return fn
@@ -781,7 +774,7 @@ def run_forward_workload(args):
     ms_per_step = elapsed_ms / K
     # the same K steps strictly one after the other on one stream (= the latency of one step)
     serial = None
-    if lanes is not None:
+    if inflight is not None:
         ms1 = ctx.timed(lambda i: step(i), K)
         serial = {"ms_per_step": ms1 / K, "value": world * B * K / (ms1 / 1e3), "unit": "clouds/s",
                   "what": "one step in flight: every replay on one stream (no all-gather); ms_per_step here is a "
@@ -887,9 +880,9 @@ def run_forward_workload(args):
                    "parallelism": ("clouds sharded by rank, no data-path collective; ONE all_gather of the ranks' "
                                    "[steps*B,256] global descriptors at the end of the timed region")
                    if world > 1 else "single GPU",
-                   "launch": graph_note + ("; two steps in flight (graph instance k on its own stream)"
-                                           if lanes is not None else ""),
-                   "steps_in_flight": 2 if lanes is not None else 1,
+                   "launch": graph_note + ("; two steps in flight (dh3d_b200.model.InFlightForward: graph instance k on "
+                                           "its own stream)" if inflight is not None else ""),
+                   "steps_in_flight": 2 if inflight is not None else 1,
                    "l2": "inputs rotate over %d resident batches; one step streams > 1 GB of activations "
                          "through the 126 MB L2, so nothing survives between steps" % R},
         "e2e": e2e,
@@ -917,7 +910,7 @@ def run_forward_workload(args):
 def run_retrieval_workload(args):
     from dh3d_b200 import _lib
     from dh3d_b200.dist import all_gather_descriptors, shard_range
-    from dh3d_b200.model import DH3D, GraphedForward, init_random_
+    from dh3d_b200.model import DH3D, GraphedForward, InFlightForward, init_random_
     from dh3d_b200.retrieval import retrieve_topk
     ctx = Ctx(args)
     torch, dev, world, rank = ctx.torch, ctx.dev, ctx.world, ctx.rank
@@ -950,40 +943,32 @@ def run_retrieval_workload(args):
         state["idx"] = idx
         return idx
 
-    def fwd_resident(i):
-        out = graphs[i % 2](dev_batches[i % R])
-        desc[i * B:(i + 1) * B].copy_(out["globaldesc"], non_blocking=True)
-
-    def fwd_e2e(i):
-        pts = host_batches[i % R].to(dev, non_blocking=True)    # H2D of this micro-batch
-        out = graphs[i % 2](pts)
-        desc[i * B:(i + 1) * B].copy_(out["globaldesc"], non_blocking=True)
-
-    # two micro-batches in flight: graph instance k replays on its own stream (see run_forward_workload); the job's tail
+    # two micro-batches in flight (model.InFlightForward: graph instance k replays on its own stream); the job's tail
     # (all-gather + retrieval) runs on the current stream once both lanes have drained
-    cur = torch.cuda.current_stream(dev)
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)] if args.in_flight == 2 else None
+    inflight = InFlightForward(graphs) if args.in_flight == 2 else None
 
-    def laned(fwd, tail):
+    def run_batch(i, pts):
+        def keep(out):
+            desc[i * B:(i + 1) * B].copy_(out["globaldesc"], non_blocking=True)
+        if inflight is None:
+            keep(graphs[i % 2](pts))
+        else:
+            inflight.submit(pts, consume=keep)
+
+    def laned(source, tail):
         def fn(i):
-            if lanes is None:
-                fwd(i)
-            else:
-                if i == 0:
-                    for s in lanes:
-                        s.wait_stream(cur)
-                with torch.cuda.stream(lanes[i % 2]):
-                    fwd(i)
-                if i == K - 1:
-                    for s in lanes:
-                        cur.wait_stream(s)
+            run_batch(i, source(i))
             if i == K - 1:
+                if inflight is not None:
+                    inflight.join()
                 tail()
         return fn
 
-    step_resident = laned(fwd_resident, finish)
-    # the job's result: [n_local, 25] neighbour ids
-    step_e2e = laned(fwd_e2e, lambda: topk_host.copy_(finish(), non_blocking=True))
+    step_resident = laned(lambda i: dev_batches[i % R], finish)
+    # end to end: H2D of each micro-batch from pinned memory (current stream; the lane waits for it), and the job's
+    # result, [n_local, 25] neighbour ids, back to the host
+    step_e2e = laned(lambda i: host_batches[i % R].to(dev, non_blocking=True),
+                     lambda: topk_host.copy_(finish(), non_blocking=True))
 
     for i in range(max(args.warmup, 3)):
         graphs[i % 2](dev_batches[i % R])
@@ -1014,9 +999,9 @@ def run_retrieval_workload(args):
                    "clouds_per_gpu": n_local, "micro_batch": B, "outputs": "globaldesc only",
                    "parallelism": "contiguous shards of clouds per rank, no data-path collective; one all_gather_into_tensor "
                                   "of [%d,256] per rank (%d KiB) then dh3d_topk_l2 k=25" % (n_local, n_local),
-                   "launch": "forward replayed from a CUDA graph" + ("; two micro-batches in flight (graph instance k on "
-                                                                      "its own stream)" if lanes is not None else ""),
-                   "steps_in_flight": 2 if lanes is not None else 1, "retrieval_self_match_first": self_first},
+                   "launch": "forward replayed from a CUDA graph" + ("; two micro-batches in flight (dh3d_b200.model."
+                                                                      "InFlightForward)" if inflight is not None else ""),
+                   "steps_in_flight": 2 if inflight is not None else 1, "retrieval_self_match_first": self_first},
         "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": B * N_POINTS * 12,
                 "d2h_bytes_per_step": n_local * 25 * 4 / K, "ms_total": ms_e2e,
                 "note": "per micro-batch: H2D of 32 clouds from pinned memory + forward; at the end one all-gather of the "

@@ -105,6 +105,31 @@ def test_graph_replay_matches_eager_bitwise():
             assert torch.equal(out[k], eager[k]), k
 
 
+@pytest.mark.timeout(300)
+def test_batches_in_flight_on_two_and_three_lanes_match_serial_bitwise():
+    """InFlightForward: graph instances replayed on their own streams, batches round robin; every batch's results (taken
+    by ``consume`` inside the lane) equal the eager forward of that batch bit for bit, in submission order."""
+    from dh3d_b200.model import InFlightForward
+    model, _ = _model(6)
+    rng = np.random.RandomState(6)
+    batches = [torch.from_numpy(make_cloud(rng, 2, 2048, extent=15.0)).cuda() for _ in range(5)]
+    want = [{k: v.clone() for k, v in model(p).items() if k in ("local_desc", "attention", "globaldesc")}
+            for p in batches]
+    torch.cuda.synchronize()
+    for lanes in (2, 3):
+        fwd = InFlightForward.build(model, batches[0], lanes=lanes)
+        got = []
+        for rep in range(3):
+            for p in batches:
+                fwd.submit(p.clone(), consume=lambda o: got.append({k: v.clone() for k, v in o.items() if k in want[0]}))
+        fwd.join()
+        torch.cuda.current_stream().synchronize()      # join() made the current stream wait for every lane
+        assert len(got) == 3 * len(batches)
+        for n, g in enumerate(got):
+            for k, v in want[n % len(batches)].items():
+                assert torch.equal(g[k], v), (lanes, n, k)
+
+
 def test_unfused_composition_matches_fused_blocks(monkeypatch):
     """The fused block kernels (dh3d_se_pool_excite, dh3d_linear_join_packed) against the per-op composition they
     replace, on the same shapes and weights: same outputs to fp32 rounding, and the composition passes the oracle

@@ -2,7 +2,8 @@
 # Final validation of round 2 (r3s): ticket-ordered NetVLAD tail + two steps in flight in bench.py.
 # Ordered by priority (the GPU budget may cut the call short); every leg writes its own file.
 out=gpurun_out; mkdir -p $out
-# 1. gate: the re-written tail (parity, B > 32, four concurrent streams).  If it fails, the rest runs on the previous tail.
+# 1. gate: the re-written tail (parity, B > 32, four concurrent streams).  If it fails, the rest runs on the previous tail
+#    (libdh3d_b200_prevtail.so was an ad-hoc build of the previous commit's netvlad.cu for this one call; the gate passed).
 timeout 200 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k netvlad > $out/pytest_r3s_netvlad.log 2>&1; rc=$?
 echo "netvlad gate rc=$rc"; tail -2 $out/pytest_r3s_netvlad.log
 if [ $rc -ne 0 ]; then

@@ -18,7 +18,9 @@ Workloads (BASELINE.json `configs`):
              achieved algorithmic HBM GB/s against the measured roofline, native and drop-in (reference-layout) entries.
 
 One JSON line on stdout (rank 0).  `value` = clouds of all ranks / max-over-ranks device time with inputs resident
-in HBM; `e2e` = the same forward through the public API from pinned HOST buffers with the H2D copy of the clouds and
+in HBM, two steps in flight per GPU (dh3d_b200.model.InFlightForward: the two CUDA-graph instances of the forward
+replay on their own streams; `--in-flight 1` = strictly one step after the other, also reported as
+`one_step_in_flight`); `e2e` = the same forward through the public API from pinned HOST buffers with the H2D copy of the clouds and
 ONE D2H copy of the step's whole result block inside the timed region, next to the measured pinned-D2H ceiling of
 the box; `e2e_modes` = the reference's two other output modes (global descriptors only; --perform_nms keypoint
 rows only); `roofline` = the dominant kernel timed live with CUDA events; `op_roofline` / `step_hbm` = every op's
